@@ -1,0 +1,187 @@
+/*
+ * pycd_b200.h -- C ABI of the B200-native PyCD hot path (libpycd_b200.so).
+ *
+ * The reference (vpasumarthi/PyCD) is pure Python and has no FFI of its own; the
+ * drop-in boundary is its driver functions (PyCD/material_setup.py:13,
+ * PyCD/material_run.py:13, PyCD/material_msd.py:13) and the files they exchange.
+ * The entry points below are what those drivers' bodies bind instead of the
+ * reference's numpy loops; each one cites the reference code it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch/numpy types.  Every bulk pointer may be a
+ *    HOST pointer (pageable or pinned) or a DEVICE pointer on the context's GPU; the
+ *    library detects which (cudaPointerGetAttributes) and stages copies itself.
+ *    Host buffers give the end-to-end path, device buffers the resident path.
+ *  - arrays are C-contiguous, caller-owned, never retained unless stated.
+ *  - every call is blocking: the context's stream is synchronised before return.
+ *  - return value 0 = ok, non-zero = error; pycd_last_error() gives the message
+ *    (thread-local).  There is NO CPU fallback: pycd_ctx_create fails without an
+ *    sm_100 device.
+ *  - units are the reference's atomic units (bohr, Hartree, a.u. time).
+ */
+#ifndef PYCD_B200_H
+#define PYCD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYCD_ABI_VERSION 1
+
+typedef struct pycd_ctx pycd_ctx;
+typedef struct pycd_kmc_system pycd_kmc_system;
+typedef struct pycd_kmc_ensemble pycd_kmc_ensemble;
+
+/* ---- context ----------------------------------------------------------- */
+int pycd_abi_version(void);
+const char *pycd_last_error(void);
+/* device = CUDA ordinal (one process per GPU: pass LOCAL_RANK). */
+int pycd_ctx_create(int device, pycd_ctx **out);
+int pycd_ctx_destroy(pycd_ctx *ctx);
+/* number of SMs, free/total bytes of the context's device */
+int pycd_ctx_info(pycd_ctx *ctx, int32_t *n_sm, int64_t *free_bytes, int64_t *total_bytes);
+/* total kernel launches issued by this context so far (bench "gpu_launches") */
+int64_t pycd_ctx_launch_count(pycd_ctx *ctx);
+/* elapsed device milliseconds (CUDA events on the context's stream) of the kernels
+ * of the most recent compute call, by kernel class: 0 = ewald fourier, 1 = ewald
+ * finish, 2 = ewald expand, 3 = kmc step kernel, 4 = msd, 5 = v_lat matvec */
+double pycd_ctx_last_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
+/* accumulated device milliseconds / launches of a kernel class since the last reset */
+double pycd_ctx_total_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
+int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t kernel_class);
+int pycd_ctx_reset_timers(pycd_ctx *ctx);
+
+/* ---- Ewald site-pair array --------------------------------------------- */
+/* Replaces System.pot_r_ewald / pot_k_ewald / get_precomputed_array
+ * (PyCD/core.py:799-878, 1594-1602, 1659-1661).  Pair vectors are never
+ * materialised: minimum images (core.py:304-361) are taken on the fly from the
+ * site coordinates, the reciprocal sum uses per-site structure factors. */
+typedef struct {
+    int64_t n_sites;       /* N */
+    const double *coords;  /* (N,3) site coordinates, bohr (Material.generate_sites, core.py:154-241) */
+    double cell[9];        /* simulation_cell_matrix rows, core.py:296 */
+    int32_t pbc[3];        /* core.py:262 */
+    double recip[9];       /* System.reciprocal_lattice_matrix rows, core.py:715-722 */
+    double volume;         /* System.system_volume, core.py:711-714 */
+    double alpha;          /* yaml alpha / ANG2BOHR, core.py:768-771 */
+    double r_cut;          /* yaml r_cut * ANG2BOHR, core.py:773-776 */
+    double k_cut;          /* yaml k_cut / ANG2BOHR, core.py:779-784 */
+    double dielectric;     /* Material.dielectric_constant */
+    int32_t k_max[3];      /* ceil(k_cut/|b_i|), core.py:1599 */
+} pycd_ewald_desc;
+
+typedef struct {
+    int64_t k_eff;         /* half-space k vectors with |k|^2 < k_cut^2 */
+    int64_t rows;          /* rows computed by this call */
+    double fourier_ms;     /* device time of the reciprocal-space kernel */
+    double finish_ms;      /* device time of real-space + self + combine */
+    double flops;          /* algorithmic flops of this call: 4*rows*N*k_eff + 40*rows*N */
+    int32_t k_split;       /* split-k factor used */
+} pycd_ewald_stats;
+
+/* out[(row_end-row_begin), N] = P[row_begin:row_end, :].  Row blocks are how the
+ * array is sharded across GPUs (rank g owns rows [gN/G,(g+1)N/G)). */
+int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64_t row_begin,
+                    int64_t row_end, double *out, pycd_ewald_stats *stats);
+
+/* Translation-symmetric expansion (valid for pbc = [1,1,1]): given
+ * Pu[n_basis, N] = P[0:n_basis, :] (the rows of unit cell 0) produce
+ * out[(row_end-row_begin), N] with P[i,j] = Pu[b_i, (cell_j - cell_i mod size)*n_basis + b_j].
+ * Site index layout core.py:402-418 (cell = (x*ny + y)*nz + z, basis fastest). */
+int pycd_ewald_expand(pycd_ctx *ctx, const double *p_unit, int32_t n_basis,
+                      const int32_t size[3], int64_t row_begin, int64_t row_end, double *out);
+
+/* ---- KMC --------------------------------------------------------------- */
+/* Static tables of one carrier type; replaces the per-step lookups of
+ * Run.get_process_attributes / get_process_rates (core.py:1946-2050) into
+ * Run.__init__'s lists (core.py:1861-1927). */
+typedef struct {
+    int64_t n_sites;            /* N */
+    const double *P;            /* (N,N) precomputed_array; a DEVICE pointer is used in place
+                                   (caller keeps it alive), a HOST pointer is copied */
+    int64_t n_centres;          /* sites of the carrier's element type */
+    const int32_t *site_centre; /* (N) element_type_element_index or -1, core.py:1935-1944 */
+    const int32_t *site_class;  /* (N) system_class_index_list, core.py:729-730 */
+    int32_t n_class;
+    int32_t nn;                 /* System.num_neighbors of the species, core.py:746-765 */
+    const int32_t *neigh;       /* (n_centres, nn) new site per slot, core.py:1964-1978 */
+    const double *hopvec;       /* (n_centres, nn, 3) hop vectors, bohr, core.py:2037-2040 */
+    const double *lam;          /* (n_class, nn) lambda per slot, core.py:1912-1917 */
+    const double *vab;          /* (n_class, nn) V_AB per slot, core.py:1918-1922 */
+    const double *e_rel;        /* (N) system_relative_energies, core.py:1717-1730 */
+    const double *q_lat;        /* (N) base_charge_config, core.py:2530-2538; V_lat = P.q_lat
+                                   is computed on the device */
+    double q_carrier;           /* species charge, core.py:1830-1832 */
+    double kT;                  /* core.py:1705 */
+    double vn;                  /* core.py:103 */
+    double field[3];            /* core.py:1749-1761 */
+    int32_t field_active;
+} pycd_kmc_system_desc;
+
+int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc *desc, pycd_kmc_system **out);
+int pycd_kmc_system_destroy(pycd_kmc_system *sys);
+/* copy V_lat (N) back (tests) */
+int pycd_kmc_system_vlat(pycd_kmc_system *sys, double *v_lat);
+
+#define PYCD_RNG_REPLAY 0 /* u1,u2 pairs supplied by the host (the reference's random.random(), core.py:2799,2802) */
+#define PYCD_RNG_PHILOX 1 /* Philox4x32-10, key = seed, counter = (step, global trajectory id) */
+
+typedef struct {
+    int64_t n_traj;            /* trajectories owned by this GPU */
+    uint64_t traj_id0;         /* global id of the first one (RNG key; results independent of sharding) */
+    int32_t n_carriers;        /* C */
+    const int32_t *occupancy0; /* (n_traj, C) initial sites, core.py:2478-2528 */
+    double dt_grid;            /* time_interval, a.u., core.py:1710 */
+    int64_t n_path;            /* int(t_final/time_interval)+1, core.py:2657 */
+    int64_t step_limit;        /* >0: stop a trajectory after this many KMC steps */
+    int32_t stop_at_grid_end;  /* 1: reference loop condition end_path_index < n_path (core.py:2787) */
+    int32_t rng_mode;
+    uint64_t seed;
+    int32_t refresh_interval;  /* 1: stateless (every rate re-gathered each step, the reference formulation);
+                                  R>1: incremental delta-E updates with a full re-gather every R steps */
+    const double *kT_traj;     /* NULL or (n_traj): per-trajectory temperature (sweeps) */
+    const double *field_traj;  /* NULL or (n_traj,3): per-trajectory field (implies field_active) */
+    int32_t record_unwrapped;  /* 1: keep the (n_traj, n_path, 3C) displacement grid on the device */
+} pycd_kmc_ensemble_desc;
+
+int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ensemble_desc *desc,
+                             pycd_kmc_ensemble **out);
+int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens);
+
+/* Advance every unfinished trajectory by at most max_steps KMC steps: rate evaluation
+ * (core.py:1989-2050), selection + time advance + recording (core.py:2796-2861).
+ * draws: REPLAY mode, (n_traj, 2*max_steps) u1,u2,...; ignored for PHILOX.
+ * events_out / times_out: NULL or (n_traj, max_steps): selected process index and
+ * simulation time after each step of this call (entries past a trajectory's end are
+ * left untouched).  steps_done: NULL or (n_traj) steps taken in this call.
+ * n_active: number of trajectories still unfinished after the call. */
+int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
+                     int32_t *events_out, double *times_out, int64_t *steps_done,
+                     int64_t *n_active);
+
+/* State read-back; any pointer may be NULL.  unwrapped: (n_traj, n_path, 3C) displacement
+ * from the start site on the time grid (unwrapped_traj.npy, core.py:2852-2854);
+ * drift: (n_traj, C, 3) sum of hop_vector*k_selected (core.py:2822-2825). */
+int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t *n_steps, double *sim_time,
+                  int32_t *occupancy, double *drift, int64_t *near_tie, int64_t *clamped,
+                  double *rates /* (n_traj, C*nn) rates of the last evaluated step */);
+/* device pointer of the resident displacement grid (input of pycd_msd without a copy) */
+int pycd_kmc_unwrapped_device(pycd_kmc_ensemble *ens, const double **dev_ptr);
+
+/* ---- MSD --------------------------------------------------------------- */
+/* Replaces the lag loop of Analysis.compute_msd (core.py:2996-3022):
+ * sd[traj,tau,c] = mean_t |r(t+tau,c)-r(t,c)|^2 * scale^2, averaged over the carriers
+ * of each type.  unwrapped: (n_traj, n_path, 3C) bohr; scale = dist_conversion;
+ * type_offsets: (n_types+1) carrier index ranges; sd_species: (n_traj, n_msd, n_types);
+ * sd_carrier: NULL or (n_traj, n_msd, C). */
+int pycd_msd(pycd_ctx *ctx, const double *unwrapped, int64_t n_traj, int64_t n_path,
+             int32_t n_carriers, int64_t n_msd, double scale, const int32_t *type_offsets,
+             int32_t n_types, double *sd_species, double *sd_carrier);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCD_B200_H */

@@ -1,0 +1,435 @@
+// ewald.cu -- fp64 Ewald site-pair array on sm_100a.
+//
+// P[i,j] = R_ij/eps + F_ij/eps - delta_ij*sqrt(alpha/pi)/eps      (PyCD/core.py:1659-1661)
+//   R_ij = erfc(sqrt(alpha) r_ij)/(2 r_ij)  for r_ij < r_cut, R_ii = 0.5   (core.py:799-814)
+//   F_ij = 2 * sum_{k in half space, |k|^2<k_cut^2} (2pi/V) exp(-k^2/4alpha) cos(k.d_ij)/k^2
+//                                                                        (core.py:853-878)
+// The reference evaluates cos(k.d_ij) per pair per k from an (N,N,3) array.  Here
+// cos(k.(r_j-r_i)) = c_i c_j + s_i s_j turns the k sum into a rank-2K update
+// F = A A^T with A[i,(k,0/1)] = sqrt-free weighted (cos,sin)(k.r_i): a GEMM whose
+// operand panels are generated on the fly in shared memory (A would be 403 GB at
+// N=30000), accumulated with DFMA in registers.  fp64 has no tcgen05 path; the
+// bound is the FP64 pipe (64 DFMA/clk/SM).
+#include "common.cuh"
+
+#include <cmath>
+#include <algorithm>
+
+namespace pycd {
+
+// one half-space k vector: integer triple + flag bit0 = "continues the previous
+// entry along n3" (phase obtained by one complex multiply instead of a sincos)
+struct __align__(8) KEntry {
+    short n1, n2, n3, flag;
+};
+
+constexpr int EW_THREADS = 256;
+
+template <int BM, int BN, int TM, int TN, int KC>
+struct EwaldTile {
+    static constexpr int TX = BN / TN;
+    static constexpr int TY = BM / TM;
+    static_assert(TX * TY == EW_THREADS, "tile/thread shape mismatch");
+    static_assert(TM % 2 == 0 && TN % 2 == 0, "double2 operand loads");
+    static constexpr size_t smem_bytes =
+        sizeof(double) * (size_t)(2 * KC) * (BM + BN) + sizeof(KEntry) * KC + sizeof(double) * KC +
+        sizeof(double) * 2 * (BM + BN);
+};
+
+// theta[j][a] = B_a . r_j  so that k_n . r_j = n1*theta_j0 + n2*theta_j1 + n3*theta_j2
+__global__ void ewald_theta_kernel(const double *__restrict__ coords, long long n,
+                                   double b00, double b01, double b02, double b10, double b11,
+                                   double b12, double b20, double b21, double b22,
+                                   double *__restrict__ theta)
+{
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double x = coords[3 * j], y = coords[3 * j + 1], z = coords[3 * j + 2];
+    theta[3 * j + 0] = b00 * x + b01 * y + b02 * z;
+    theta[3 * j + 1] = b10 * x + b11 * y + b12 * z;
+    theta[3 * j + 2] = b20 * x + b21 * y + b22 * z;
+}
+
+// Reciprocal-space partial sums.  grid = k_split * n_row_tiles * n_col_tiles CTAs of
+// 256 threads; CTA (ks, rt, ct) accumulates its share of the k chunks for the
+// BM x BN tile and writes out[ks][row][col] (un-scaled: sum_k w_k cos(k.d_ij)).
+template <int BM, int BN, int TM, int TN, int KC, int SUB>
+__global__ void __launch_bounds__(EW_THREADS, 1)
+ewald_fourier_kernel(const double *__restrict__ theta, long long n_sites, long long row0,
+                     long long n_rows, const KEntry *__restrict__ kent,
+                     const double *__restrict__ kw, int n_chunks, int k_split, int n_row_tiles,
+                     int n_col_tiles, double *__restrict__ out)
+{
+    using T = EwaldTile<BM, BN, TM, TN, KC>;
+    constexpr int TX = T::TX, TY = T::TY;
+    constexpr int NS = BM + BN;
+    static_assert(KC % SUB == 0, "sub-chunk must divide chunk");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);  // [2*KC][BM]  rows, weighted
+    double *Bs = As + 2 * KC * BM;                       // [2*KC][BN]  columns
+    double *s_w = Bs + 2 * KC * BN;                      // [KC]
+    double *s_z3 = s_w + KC;                             // [NS][2]  e^{i theta_3} per tile site
+    KEntry *s_ent = reinterpret_cast<KEntry *>(s_z3 + 2 * NS);  // [KC]
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    int bid = blockIdx.x;
+    const int ct = bid % n_col_tiles; bid /= n_col_tiles;
+    const int rt = bid % n_row_tiles; bid /= n_row_tiles;
+    const int ks = bid;
+    const int c0 = (int)(((long long)ks * n_chunks) / k_split);
+    const int c1 = (int)(((long long)(ks + 1) * n_chunks) / k_split);
+
+    // tile-site -> global site (clamped; out-of-range results are never stored)
+    auto tile_site = [&](int sl) -> long long {
+        long long s = (sl < BM) ? (row0 + (long long)rt * BM + sl) : ((long long)ct * BN + (sl - BM));
+        return s < n_sites ? s : n_sites - 1;
+    };
+    for (int sl = tid; sl < NS; sl += EW_THREADS) {
+        double s3, c3;
+        sincos(theta[3 * tile_site(sl) + 2], &s3, &c3);
+        s_z3[2 * sl] = c3;
+        s_z3[2 * sl + 1] = s3;
+    }
+
+    double acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+
+    for (int chunk = c0; chunk < c1; ++chunk) {
+        __syncthreads();  // previous product finished with the panels
+        if (tid < KC) {
+            s_ent[tid] = kent[(long long)chunk * KC + tid];
+            s_w[tid] = kw[(long long)chunk * KC + tid];
+        }
+        __syncthreads();
+        // ---- generate panels: item = (tile site, sub-chunk of SUB consecutive k) ----
+        for (int item = tid; item < NS * (KC / SUB); item += EW_THREADS) {
+            const int sl = item % NS, sub = item / NS;
+            const long long site = tile_site(sl);
+            const double t1 = theta[3 * site], t2 = theta[3 * site + 1], t3 = theta[3 * site + 2];
+            const double c3 = s_z3[2 * sl], s3 = s_z3[2 * sl + 1];
+            double c = 1.0, s = 0.0;
+#pragma unroll 4
+            for (int e = sub * SUB; e < (sub + 1) * SUB; ++e) {
+                const KEntry ke = s_ent[e];
+                if (e == sub * SUB || !(ke.flag & 1)) {
+                    const double arg = fma((double)ke.n1, t1, fma((double)ke.n2, t2, (double)ke.n3 * t3));
+                    sincos(arg, &s, &c);
+                } else {
+                    const double cn = c * c3 - s * s3;
+                    s = s * c3 + c * s3;
+                    c = cn;
+                }
+                if (sl < BM) {
+                    const double w = s_w[e];
+                    As[e * BM + sl] = w * c;
+                    As[(KC + e) * BM + sl] = w * s;
+                } else {
+                    Bs[e * BN + (sl - BM)] = c;
+                    Bs[(KC + e) * BN + (sl - BM)] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- rank-2KC update of the register tile ----
+#pragma unroll 4
+        for (int kk = 0; kk < 2 * KC; ++kk) {
+            double a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM / 2; ++i) {
+                const double2 v = *reinterpret_cast<const double2 *>(&As[kk * BM + i * 2 * TY + 2 * ty]);
+                a[2 * i] = v.x;
+                a[2 * i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < TN / 2; ++j) {
+                const double2 v = *reinterpret_cast<const double2 *>(&Bs[kk * BN + j * 2 * TX + 2 * tx]);
+                b[2 * j] = v.x;
+                b[2 * j + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+
+    double *o = out + (long long)ks * n_rows * n_sites;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long row = (long long)rt * BM + (i / 2) * 2 * TY + 2 * ty + (i & 1);
+        if (row >= n_rows) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const long long col = (long long)ct * BN + (j / 2) * 2 * TX + 2 * tx + (j & 1);
+            if (col < n_sites) o[row * n_sites + col] = acc[i][j];
+        }
+    }
+}
+
+struct FinishParams {
+    double cell[9], cellinv[9];
+    int pbc[3];
+    double sqrt_alpha, r_cut, eps, self_term;
+};
+
+// Real-space term with the reference's 27-image minimum-image search
+// (core.py:304-361), self term and the final combination (core.py:1594-1602,
+// 1659-1661), fused with the split-k reduction.
+__global__ void __launch_bounds__(256)
+ewald_finish_kernel(const double *__restrict__ coords, long long n_sites, long long row0,
+                    long long n_rows, FinishParams fp, const double *partials, int k_split,
+                    double *out)
+{
+    const long long total = n_rows * n_sites;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long il = idx / n_sites, j = idx - il * n_sites, i = row0 + il;
+        double f = 0.0;
+        for (int s = 0; s < k_split; ++s) f += partials[(long long)s * total + idx];
+        const double dx = coords[3 * j] - coords[3 * i], dy = coords[3 * j + 1] - coords[3 * i + 1],
+                     dz = coords[3 * j + 2] - coords[3 * i + 2];
+        double fr[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            fr[k] = dx * fp.cellinv[k] + dy * fp.cellinv[3 + k] + dz * fp.cellinv[6 + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (fp.pbc[k]) fr[k] -= rint(fr[k]);
+        double best2 = 1e300;
+#pragma unroll
+        for (int ox = -1; ox <= 1; ++ox)
+#pragma unroll
+            for (int oy = -1; oy <= 1; ++oy)
+#pragma unroll
+                for (int oz = -1; oz <= 1; ++oz) {
+                    const double tx = fr[0] + (fp.pbc[0] ? ox : 0), ty = fr[1] + (fp.pbc[1] ? oy : 0),
+                                 tz = fr[2] + (fp.pbc[2] ? oz : 0);
+                    const double x = tx * fp.cell[0] + ty * fp.cell[3] + tz * fp.cell[6];
+                    const double y = tx * fp.cell[1] + ty * fp.cell[4] + tz * fp.cell[7];
+                    const double z = tx * fp.cell[2] + ty * fp.cell[5] + tz * fp.cell[8];
+                    const double r2 = x * x + y * y + z * z;
+                    best2 = r2 < best2 ? r2 : best2;
+                }
+        const double r = sqrt(best2);
+        double real = 0.0;
+        if (r < fp.r_cut) real = (erfc(fp.sqrt_alpha * r) / 2) / (i == j ? 1.0 : r);
+        out[idx] = real / fp.eps + (f * 2) / fp.eps + (i == j ? fp.self_term : 0.0);
+    }
+}
+
+// P[i,j] = Pu[b_i][(cell_j - cell_i mod size)*nb + b_j]
+__global__ void __launch_bounds__(256)
+ewald_expand_kernel(const double *__restrict__ pu, int nb, int sx, int sy, int sz,
+                    long long n_sites, long long row0, long long n_rows, double *__restrict__ out)
+{
+    const long long total = n_rows * n_sites;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long il = idx / n_sites;
+        const int j = (int)(idx - il * n_sites), i = (int)(row0 + il);
+        const int ci = i / nb, bi = i - ci * nb, cj = j / nb, bj = j - cj * nb;
+        const int zi = ci % sz, yi = (ci / sz) % sy, xi = ci / (sz * sy);
+        const int zj = cj % sz, yj = (cj / sz) % sy, xj = cj / (sz * sy);
+        int ddx = xj - xi, ddy = yj - yi, ddz = zj - zi;
+        ddx += ddx < 0 ? sx : 0;
+        ddy += ddy < 0 ? sy : 0;
+        ddz += ddz < 0 ? sz : 0;
+        const int dc = (ddx * sy + ddy) * sz + ddz;
+        out[idx] = pu[(long long)bi * n_sites + (long long)dc * nb + bj];
+    }
+}
+
+static void invert3(const double *m, double *inv) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    PYCD_REQUIRE(det != 0.0, "singular simulation cell");
+    inv[0] = (e * i - f * h) / det; inv[1] = (c * h - b * i) / det; inv[2] = (b * f - c * e) / det;
+    inv[3] = (f * g - d * i) / det; inv[4] = (a * i - c * g) / det; inv[5] = (c * d - a * f) / det;
+    inv[6] = (d * h - e * g) / det; inv[7] = (b * g - a * h) / det; inv[8] = (a * e - b * d) / det;
+}
+
+// Half-space k list ordered in (n1,n2) columns with n3 ascending, padded to a
+// multiple of kc with zero-weight entries.  Any half space gives the same sum
+// (cos is even); the reference keeps the lexicographically negative triples
+// (core.py:816-838), here the half space is n3>0 | (n3==0,n2>0) | (n3==n2==0,n1>0)
+// so that runs along n3 are contiguous.
+static int64_t build_k_list(const pycd_ewald_desc &d, int kc, int sub, std::vector<KEntry> &ent,
+                            std::vector<double> &w) {
+    const double alpha4 = 4 * d.alpha;
+    const double coeff = (2 * M_PI) / d.volume;
+    const double kc2 = d.k_cut * d.k_cut;
+    PYCD_REQUIRE(d.k_max[0] < 32000 && d.k_max[1] < 32000 && d.k_max[2] < 32000, "k_max too large");
+    ent.clear();
+    w.clear();
+    for (int n1 = -d.k_max[0]; n1 <= d.k_max[0]; ++n1)
+        for (int n2 = -d.k_max[1]; n2 <= d.k_max[1]; ++n2) {
+            int prev = INT32_MIN;
+            for (int n3 = 0; n3 <= d.k_max[2]; ++n3) {
+                if (n3 == 0 && !(n2 > 0 || (n2 == 0 && n1 > 0))) continue;
+                double kv[3];
+                for (int c = 0; c < 3; ++c)
+                    kv[c] = n1 * d.recip[0 * 3 + c] + n2 * d.recip[1 * 3 + c] + n3 * d.recip[2 * 3 + c];
+                const double k2 = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+                if (!(k2 < kc2)) continue;
+                KEntry e;
+                e.n1 = (short)n1; e.n2 = (short)n2; e.n3 = (short)n3;
+                const bool cont = (prev == n3 - 1) && (ent.size() % (size_t)sub != 0);
+                e.flag = cont ? 1 : 0;
+                ent.push_back(e);
+                w.push_back(coeff * exp(-k2 / alpha4) / k2);  // core.py:869-875
+                prev = n3;
+            }
+        }
+    const int64_t k_eff = (int64_t)ent.size();
+    while (ent.size() % (size_t)kc != 0) {
+        KEntry e = {0, 0, 0, 0};
+        ent.push_back(e);
+        w.push_back(0.0);
+    }
+    return k_eff;
+}
+
+template <int BM, int BN, int TM, int TN, int KC, int SUB>
+static void launch_fourier(pycd_ctx *ctx, const double *theta, long long n, long long row0,
+                           long long n_rows, const KEntry *kent, const double *kw, int n_chunks,
+                           int k_split, double *out) {
+    using T = EwaldTile<BM, BN, TM, TN, KC>;
+    auto kern = ewald_fourier_kernel<BM, BN, TM, TN, KC, SUB>;
+    PYCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::smem_bytes));
+    const int n_row_tiles = (int)((n_rows + BM - 1) / BM), n_col_tiles = (int)((n + BN - 1) / BN);
+    const long long grid = (long long)k_split * n_row_tiles * n_col_tiles;
+    PYCD_REQUIRE(grid < (1ll << 31), "grid too large");
+    kern<<<(unsigned)grid, EW_THREADS, T::smem_bytes, ctx->stream>>>(
+        theta, n, row0, n_rows, kent, kw, n_chunks, k_split, n_row_tiles, n_col_tiles, out);
+    check_launch(ctx, "ewald_fourier_kernel");
+}
+
+}  // namespace pycd
+
+using namespace pycd;
+
+extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64_t row_begin,
+                               int64_t row_end, double *out, pycd_ewald_stats *stats) {
+    return guarded([&] {
+        PYCD_REQUIRE(ctx && desc && out, "NULL argument");
+        const long long n = desc->n_sites;
+        PYCD_REQUIRE(n > 0 && row_begin >= 0 && row_end <= n && row_begin < row_end, "bad row range");
+        PYCD_REQUIRE(desc->alpha > 0 && desc->volume > 0 && desc->dielectric > 0, "bad Ewald parameters");
+        DeviceGuard g(ctx);
+        const long long n_rows = row_end - row_begin;
+        constexpr int KC = 32;
+        // wide tile for big row blocks, skinny tile (rows of one unit cell) otherwise
+        const bool wide = n_rows > 64;
+        const int sub = wide ? 32 : 8;
+
+        std::vector<KEntry> ent;
+        std::vector<double> w;
+        const int64_t k_eff = build_k_list(*desc, KC, sub, ent, w);
+        const int n_chunks = (int)(ent.size() / KC);
+
+        InBuf<double> coords;
+        coords.bind(desc->coords, (size_t)n * 3, ctx->stream);
+        DevBuf<double> theta, kw;
+        DevBuf<KEntry> kent;
+        theta.alloc((size_t)n * 3);
+        const double *B = desc->recip;
+        ewald_theta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            coords.p, n, B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], B[8], theta.p);
+        check_launch(ctx, "ewald_theta_kernel");
+        OutBuf<double> o;
+        o.bind(out, (size_t)n_rows * n);
+
+        int k_split = 1;
+        if (n_chunks > 0) {
+            kent.alloc(ent.size());
+            kw.alloc(w.size());
+            PYCD_CUDA(cudaMemcpyAsync(kent.p, ent.data(), ent.size() * sizeof(KEntry),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+            PYCD_CUDA(cudaMemcpyAsync(kw.p, w.data(), w.size() * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+            const long long bm = wide ? 128 : 32, bn = wide ? 128 : 256;
+            const long long tiles = ((n_rows + bm - 1) / bm) * ((n + bn - 1) / bn);
+            long long want = (2ll * ctx->n_sm + tiles - 1) / tiles;
+            const long long ws_cap = (1ll << 30) / (n_rows * n * 8) > 0 ? (1ll << 30) / (n_rows * n * 8) : 1;
+            k_split = (int)std::max(1ll, std::min({want, (long long)n_chunks, ws_cap}));
+        }
+        DevBuf<double> ws;
+        double *partials = o.dev();
+        if (k_split > 1) {
+            ws.alloc((size_t)k_split * n_rows * n);
+            partials = ws.p;
+        }
+        KernelTimer tf(ctx, KC_EWALD_FOURIER);
+        if (n_chunks > 0) {
+            if (wide)
+                launch_fourier<128, 128, 8, 8, KC, 32>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                      n_chunks, k_split, partials);
+            else
+                launch_fourier<32, 256, 8, 4, KC, 8>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                    n_chunks, k_split, partials);
+        } else {
+            PYCD_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * n_rows * n, ctx->stream));
+        }
+        tf.stop(n_chunks > 0 ? 1 : 0);
+
+        FinishParams fp;
+        for (int k = 0; k < 9; ++k) fp.cell[k] = desc->cell[k];
+        invert3(desc->cell, fp.cellinv);
+        for (int k = 0; k < 3; ++k) fp.pbc[k] = desc->pbc[k];
+        fp.sqrt_alpha = sqrt(desc->alpha);
+        fp.r_cut = desc->r_cut;
+        fp.eps = desc->dielectric;
+        fp.self_term = -sqrt(desc->alpha / M_PI) / desc->dielectric;  // core.py:1659
+        KernelTimer tr(ctx, KC_EWALD_FINISH);
+        const long long total = n_rows * n;
+        const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->n_sm * 16);
+        ewald_finish_kernel<<<blocks, 256, 0, ctx->stream>>>(coords.p, n, row_begin, n_rows, fp, partials,
+                                                             k_split, o.dev());
+        check_launch(ctx, "ewald_finish_kernel");
+        tr.stop(1);
+        o.finish(ctx->stream);
+        PYCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        tf.read();
+        tr.read();
+        if (stats) {
+            stats->k_eff = k_eff;
+            stats->rows = n_rows;
+            stats->fourier_ms = ctx->last_ms[KC_EWALD_FOURIER];
+            stats->finish_ms = ctx->last_ms[KC_EWALD_FINISH];
+            stats->flops = 4.0 * (double)n_rows * (double)n * (double)k_eff + 40.0 * (double)n_rows * (double)n;
+            stats->k_split = k_split;
+        }
+    });
+}
+
+extern "C" int pycd_ewald_expand(pycd_ctx *ctx, const double *p_unit, int32_t n_basis,
+                                 const int32_t size[3], int64_t row_begin, int64_t row_end,
+                                 double *out) {
+    return guarded([&] {
+        PYCD_REQUIRE(ctx && p_unit && size && out, "NULL argument");
+        PYCD_REQUIRE(n_basis > 0 && size[0] > 0 && size[1] > 0 && size[2] > 0, "bad supercell");
+        const long long n = (long long)n_basis * size[0] * size[1] * size[2];
+        PYCD_REQUIRE(n < (1ll << 31), "too many sites");
+        PYCD_REQUIRE(row_begin >= 0 && row_end <= n && row_begin < row_end, "bad row range");
+        DeviceGuard g(ctx);
+        const long long n_rows = row_end - row_begin;
+        InBuf<double> pu;
+        pu.bind(p_unit, (size_t)n_basis * n, ctx->stream);
+        OutBuf<double> o;
+        o.bind(out, (size_t)n_rows * n);
+        KernelTimer t(ctx, KC_EWALD_EXPAND);
+        const long long total = n_rows * n;
+        const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->n_sm * 32);
+        ewald_expand_kernel<<<blocks, 256, 0, ctx->stream>>>(pu.p, n_basis, size[0], size[1], size[2], n,
+                                                             row_begin, n_rows, o.dev());
+        check_launch(ctx, "ewald_expand_kernel");
+        t.stop(1);
+        o.finish(ctx->stream);
+        PYCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        t.read();
+    });
+}
