@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's
+golden vectors.  Needs a B200: `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle as O
+from pycd_b200 import _native as nat
+from pycd_b200 import constants
+from pycd_b200 import ewald as EW
+from pycd_b200 import kmc as K
+from pycd_b200 import msd as M
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- Ewald ----------
+@pytest.mark.parametrize('name,k_eff', [('hematite', 3457), ('bvo', 1557)])
+@pytest.mark.parametrize('symmetric', [False, True])
+def test_ewald_matches_shipped_array(ctx, name, k_eff, symmetric):
+    """north_star tolerance: 1e-10 relative in fp64 (norm of SURVEY A.2)."""
+    ex = H.load_example(name)
+    ep = H.ewald_parameters(ex)
+    P, stats = EW.precomputed_array(ctx, ep, coords=H.shipped_coords(ex), symmetric=symmetric)
+    assert stats['k_eff'] == k_eff
+    scale = np.abs(ex.P).max()
+    assert np.abs(P - ex.P).max() <= 1e-10 * scale
+    assert np.allclose(P, ex.P, rtol=1e-10, atol=1e-12 * scale)
+
+
+def test_ewald_row_blocks_equal_full(ctx):
+    ex = H.load_example('hematite')
+    ep = H.ewald_parameters(ex)
+    coords = H.shipped_coords(ex)
+    full, _ = EW.precomputed_array(ctx, ep, coords=coords, symmetric=False)
+    n = ex.supercell.num_system_elements
+    for r0, r1 in ((0, 30), (30, 97), (97, n)):
+        blk, _ = EW.ewald_rows(ctx, ep, coords, r0, r1)
+        assert np.array_equal(blk, full[r0:r1]) or np.abs(blk - full[r0:r1]).max() < 1e-16
+
+
+def test_ewald_vs_oracle_fresh_geometry_3x3x2(ctx):
+    """Fresh coordinates (no shipped files): CUDA vs the literal oracle, dense and symmetric."""
+    from types import SimpleNamespace
+    from pycd_b200.lattice import Supercell
+    ex = H.load_example('bvo')
+    sc = Supercell(ex.lattice, [3, 3, 2], [1, 1, 1])
+    ep = EW.EwaldParameters(sc, ex.cfg['alpha'], ex.cfg['r_cut'], ex.cfg['k_cut'])
+    pair = O.pairwise(sc.coordinates, sc.cell_matrix, sc.cell_matrix_inv, sc.pbc)
+    ref, keff = O.ewald_literal(pair, sc.reciprocal_lattice_matrix, sc.system_volume, ep.alpha, ep.r_cut,
+                                ep.k_cut, ep.dielectric, ep.k_max)
+    scale = np.abs(ref).max()
+    for symmetric in (False, True):
+        P, stats = EW.precomputed_array(ctx, ep, symmetric=symmetric)
+        assert stats['k_eff'] == keff
+        assert np.abs(P - ref).max() <= 1e-10 * scale
+        assert np.allclose(P, ref, rtol=1e-10, atol=1e-12 * scale)
+
+
+def test_ewald_partial_pbc_vs_oracle(ctx):
+    from pycd_b200.lattice import Supercell
+    ex = H.load_example('hematite')
+    sc = Supercell(ex.lattice, [2, 2, 1], [1, 1, 0])
+    ep = EW.EwaldParameters(sc, ex.cfg['alpha'], ex.cfg['r_cut'], ex.cfg['k_cut'])
+    pair = O.pairwise(sc.coordinates, sc.cell_matrix, sc.cell_matrix_inv, sc.pbc)
+    ref, _ = O.ewald_literal(pair, sc.reciprocal_lattice_matrix, sc.system_volume, ep.alpha, ep.r_cut,
+                             ep.k_cut, ep.dielectric, ep.k_max)
+    P, _ = EW.precomputed_array(ctx, ep)
+    assert np.abs(P - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------- KMC ------------
+def _gpu_replay(ctx, ex, run, rng, n_events_hint, chunk=32768):
+    occ = run.initial_occupancy_from(rng)
+    system = K.KmcSystem(ctx, run, ex.P)
+    state, times, events = K.run_replay(system, [rng], np.array([occ]), chunk_steps=chunk,
+                                        want_times=True, want_events=True)
+    system.close()
+    return occ, state, times[0], events[0]
+
+
+@pytest.mark.parametrize('name,n_events', [('hematite', 319946), ('bvo', 35201)])
+def test_shipped_trajectory_replay_is_bit_exact(ctx, name, n_events):
+    """Given the reference's own MT19937 draws, the event sequence is identical to the
+    shipped trajectory (unwrapped_traj.npy bit-equal), times to 1e-12 relative."""
+    ex = H.load_example(name)
+    run = H.run_parameters(ex)
+    occ, state, times, events = _gpu_replay(ctx, ex, run, H.shipped_rng(ex), n_events)
+    assert int(state['n_steps'][0]) == n_events
+    assert int(state['clamped'][0]) == 0
+    gold = H.shipped_unwrapped(ex)
+    assert np.array_equal(state['unwrapped'][0], gold)
+    n, idx, val = H.shipped_time_sample(ex)
+    assert len(times) == n
+    assert np.allclose(times[idx], val, rtol=1e-12, atol=0)
+    # same events as the oracle, step by step
+    rng = H.shipped_rng(ex)
+    occ2 = run.initial_occupancy_from(rng)
+    assert occ2 == occ
+    res = O.KmcOracle(run, ex.P).trajectory(occ2, H.draw_stream(rng, n_events + 8), want_events=True)
+    assert np.array_equal(res['events'], events)
+
+
+@pytest.mark.parametrize('tag', ['hematite_4e', 'hematite_4e_field', 'bvo_4e', 'bvo_2h'])
+def test_reference_generated_cases(ctx, tag):
+    ex, z = H.load_ref_case(tag)
+    run = H.run_parameters(ex)
+    n_traj = int(z['n_traj'])
+    rngs = [H.rng_from_state_bytes(z[f'rnd_state_{i}']) for i in range(n_traj)]
+    occ = np.array([run.initial_occupancy_from(r) for r in rngs])
+    assert list(occ[0]) == list(z['occ0'])
+    system = K.KmcSystem(ctx, run, ex.P)
+    # first-step rates against the reference's own get_process_rates
+    probe = K.KmcEnsemble(system, occ[:1], rng_mode=nat.RNG_REPLAY)
+    probe.advance(1, draws=np.full((1, 2), 0.5))
+    rates = probe.read(unwrapped=False, rates=True)['rates'][0]
+    probe.close()
+    assert np.allclose(rates, z['rates0'], rtol=5e-12, atol=0)
+    state, times, _ = K.run_replay(system, rngs, occ, chunk_steps=16384, want_times=True)
+    for i in range(n_traj):
+        assert int(state['n_steps'][i]) == int(z[f'time_n_{i}']) - 1
+        assert np.array_equal(state['unwrapped'][i], z[f'unwrapped_{i}'])
+        assert np.allclose(times[i][z[f'time_index_{i}']], z[f'time_value_{i}'], rtol=1e-12, atol=0)
+    if 'drift_mobility' in z.files:
+        mob = K.drift_mobility(state['drift'], run.field, run.field_mag)
+        assert np.allclose(mob, z['drift_mobility'], rtol=1e-10)
+    system.close()
+
+
+def test_vlat_matches_oracle(ctx):
+    ex = H.load_example('bvo')
+    run = H.run_parameters(ex)
+    system = K.KmcSystem(ctx, run, ex.P)
+    assert np.allclose(system.v_lat(), O.vlat(ex.P, run.q_lat), rtol=0, atol=2e-16 * np.abs(ex.P).max() * 50)
+    system.close()
+
+
+def _philox_case(name='hematite', species=(8, 0), size=None):
+    ex = H.load_example(name, species_count=list(species))
+    return ex, H.run_parameters(ex)
+
+
+@pytest.mark.parametrize('refresh', [1, 16])
+def test_philox_ensemble_matches_oracle(ctx, refresh):
+    """Counter-based RNG mode: 64 trajectories x 8 carriers, fixed 3000 steps; stateless and
+    incremental delta-E updates give the oracle's event sequences (final sites, step counts,
+    displacement grids bit-equal)."""
+    ex, run = _philox_case()
+    n_traj, steps = 64, 3008
+    occ = K.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed=11)
+    dt, n_path = run.time_interval / 200, 400
+    system = K.KmcSystem(ctx, run, ex.P)
+    ens = K.KmcEnsemble(system, occ, dt_grid=dt, n_path=n_path, step_limit=steps, stop_at_grid_end=False,
+                        rng_mode=nat.RNG_PHILOX, seed=11, refresh_interval=refresh)
+    while ens.advance_resident(1504) > 0:
+        pass
+    got = ens.read()
+    ens.close()
+    system.close()
+    ref = O.KmcOracle(run, ex.P, dt_grid=dt, n_path=n_path, step_limit=steps, stop_at_grid_end=False,
+                      rng_mode=1, seed=11).ensemble(occ)
+    assert np.array_equal(got['n_steps'], ref['n_steps'])
+    assert np.array_equal(got['occupancy'], ref['occupancy'])
+    assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+
+
+def test_sharding_is_invisible(ctx):
+    """Trajectories keyed by global id: running [0,32) and [32,64) separately equals [0,64)."""
+    ex, run = _philox_case(species=(4, 0))
+    occ = K.philox_initial_occupancy(run.tables, 64, run.n_carriers, seed=3)
+    system = K.KmcSystem(ctx, run, ex.P)
+
+    def go(lo, hi):
+        ens = K.KmcEnsemble(system, occ[lo:hi], step_limit=2000, stop_at_grid_end=False, n_path=64,
+                            dt_grid=run.time_interval / 50, rng_mode=nat.RNG_PHILOX, seed=3, traj_id0=lo)
+        while ens.advance_resident(1000) > 0:
+            pass
+        out = ens.read()
+        ens.close()
+        return out
+    whole, a, b = go(0, 64), go(0, 32), go(32, 64)
+    assert np.array_equal(whole['unwrapped'], np.concatenate([a['unwrapped'], b['unwrapped']]))
+    assert np.array_equal(whole['occupancy'], np.concatenate([a['occupancy'], b['occupancy']]))
+    system.close()
+
+
+def test_per_trajectory_conditions(ctx):
+    """Sweep mode: per-trajectory kT / field equal separate single-condition runs."""
+    ex, run = _philox_case(species=(4, 0))
+    occ = K.philox_initial_occupancy(run.tables, 8, run.n_carriers, seed=5)
+    kTs = np.array([250, 300, 350, 400] * 2) * constants.K2AUTEMP
+    fields = np.zeros((8, 3))
+    fields[4:, 0] = 1e-4
+    system = K.KmcSystem(ctx, run, ex.P)
+    kw = dict(step_limit=1500, stop_at_grid_end=False, n_path=32, dt_grid=run.time_interval / 20,
+              rng_mode=nat.RNG_PHILOX, seed=5)
+    ens = K.KmcEnsemble(system, occ, kT_traj=kTs, field_traj=fields, **kw)
+    ens.advance_resident(1500)
+    got = ens.read()
+    ens.close()
+    system.close()
+    for i in range(8):
+        ref = O.KmcOracle(run, ex.P, kT=kTs[i], field=fields[i], step_limit=1500, stop_at_grid_end=False,
+                          n_path=32, dt_grid=run.time_interval / 20, rng_mode=1, seed=5
+                          ).trajectory(occ[i], traj_id=i)
+        assert np.array_equal(got['occupancy'][i], ref['occupancy'])
+        assert np.array_equal(got['unwrapped'][i], ref['unwrapped'])
+        assert np.allclose(got['drift'][i], ref['drift'], rtol=1e-10, atol=1e-300)
+
+
+def test_many_processes_per_thread(ctx):
+    """n_proc > 256 (several processes per thread): 80 electrons on Hematite 2x2x1... the
+    sublattice has 48 sites, carriers may share sites (no exclusion)."""
+    ex = H.load_example('hematite', species_count=[40, 0])
+    run = H.run_parameters(ex)
+    run.n_carriers = 80
+    run.n_proc = 80 * run.tables.nn
+    rng = np.random.default_rng(0)
+    occ = run.tables.sites[rng.integers(0, run.tables.n_centres, size=(4, 80))].astype(np.int32)
+    system = K.KmcSystem(ctx, run, ex.P)
+    kw = dict(step_limit=400, stop_at_grid_end=False, n_path=16, dt_grid=run.time_interval / 100)
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=1, **kw)
+    ens.advance_resident(400)
+    got = ens.read()
+    ens.close()
+    system.close()
+    ref = O.KmcOracle(run, ex.P, rng_mode=1, seed=1, **kw).ensemble(occ)
+    assert np.array_equal(got['occupancy'], ref['occupancy'])
+    assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+
+
+# ---------------------------------------------------------------- MSD ------------
+@pytest.mark.parametrize('name', ['hematite', 'bvo'])
+def test_msd_matches_reference_on_shipped_trajectory(ctx, name):
+    ex = H.load_example(name)
+    z = np.load(H.GOLD / f'ref_msd_{name}.npz')
+    sim = ex.sim
+    mp = M.MsdParameters(sim['n_dim'], sim['species_count'], 1, sim['t_final'], sim['time_interval'],
+                         sim['msd_t_final'], sim['trim_length'], sim['temp'], sim['repr_time'], sim['repr_dist'])
+    uw = H.shipped_unwrapped(ex)[None]
+    avg = M.species_avg_sd(ctx, uw, 1, mp.n_path, mp.total_species, mp.n_msd, mp.dist_conversion, mp.type_offsets)
+    res = M.analyse(mp, avg)
+    assert np.allclose(res['msd_data'], z['msd_data'], rtol=1e-11, atol=1e-9)
+    want = float(str(z['log']).splitlines()[0].split('is:')[1].split()[0])
+    assert f"{res['diffusivity'][0]:.3e}" == f'{want:.3e}'
+
+
+def test_msd_multi_trajectory_multi_carrier(ctx):
+    ex, z = H.load_ref_case('hematite_4e')
+    sim = ex.sim
+    mp = M.MsdParameters(sim['n_dim'], sim['species_count'], 2, sim['t_final'], sim['time_interval'],
+                         sim['msd_t_final'], sim['trim_length'], sim['temp'], sim['repr_time'], sim['repr_dist'])
+    uw = np.stack([z['unwrapped_0'], z['unwrapped_1']])
+    avg, car = M.species_avg_sd(ctx, uw, 2, mp.n_path, mp.total_species, mp.n_msd, mp.dist_conversion,
+                                mp.type_offsets, want_carrier=True)
+    pos = uw.reshape(2, mp.n_path, 4, 3) * mp.dist_conversion
+    assert np.allclose(car, O.msd_sd(pos, mp.n_msd), rtol=1e-12, atol=1e-12)
+    res = M.analyse(mp, avg)
+    assert np.allclose(res['msd_data'], z['msd_data'], rtol=1e-11, atol=1e-9)
+    lines = str(z['msd_log']).splitlines()
+    assert f"{res['diffusivity'][0]:.3e}" == f"{float(lines[0].split('is:')[1].split()[0]):.3e}"
+    assert f"{res['diffusivity_sem'][0]:.3e}" == f"{float(lines[1].split('is:')[1].split()[0]):.3e}"
+
+
+def test_errors_are_loud(ctx):
+    ex = H.load_example('hematite')
+    run = H.run_parameters(ex)
+    system = K.KmcSystem(ctx, run, ex.P)
+    with pytest.raises(nat.NativeError):
+        K.KmcEnsemble(system, np.array([[10 ** 6]]))  # out of range
+    with pytest.raises(nat.NativeError):
+        K.KmcEnsemble(system, np.array([[ex.supercell.num_system_elements - 1]]))  # an O site
+    system.close()
