@@ -1,0 +1,230 @@
+"""Host logic that needs no GPU: constants, geometry, tables, file formats, the C-ABI
+library's exported symbols (no compute calls)."""
+import ctypes
+import pickle
+import random
+import re
+import subprocess
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import yaml
+
+import helpers as H
+from pycd_b200 import _native as nat
+from pycd_b200 import constants
+from pycd_b200 import kmc as K
+from pycd_b200.ewald import EwaldParameters, log_prefix
+from pycd_b200.fileio import format_elapsed, generate_report, read_poscar
+from pycd_b200.lattice import Lattice, Supercell
+from pycd_b200.tables import HopTables, load_hop_neighbor_list, save_hop_neighbor_list
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_constants_pinned():
+    # SURVEY appendix A.1 values of the reference's PyCD/constants.py
+    assert constants.ANG2BOHR == 1.8897261264678997
+    assert constants.EV2HARTREE == 0.03674932246011127
+    assert constants.SEC2AUTIME == 4.134137336634339e16
+    assert 300 * constants.K2AUTEMP == 9.500431539230842e-4
+
+
+def test_poscar_and_lattice():
+    ex = H.load_example('hematite')
+    lat = ex.lattice
+    assert lat.element_types == ['Fe', 'O']
+    assert list(lat.n_elements_per_unit_cell) == [12, 18]
+    z = lat.fractional_unit_cell_coords
+    assert np.all(np.diff(z[:12, 2]) >= 0) and np.all(np.diff(z[12:, 2]) >= 0)
+    assert lat.vn == 1.85e13 / constants.SEC2AUTIME
+    assert lat.lambda_values['Fe:Fe'][0][0] == 1.74533 * constants.EV2HARTREE
+    assert lat.hop_element_types == {'electron': ['Fe:Fe'], 'hole': ['O:O']}
+    bvo = H.load_example('bvo').lattice
+    assert bvo.num_classes == [2, 1, 1]
+    # stable z-sort: BVO O classes alternate by z-layer (shipped order)
+    assert sorted(set(bvo.unit_cell_class_list[:16])) == [0, 1]
+
+
+def test_site_index_layout():
+    """cell = (x*ny + y)*nz + z, basis fastest (reference tests/test_neighbors.py:54-80)."""
+    ex = H.load_example('hematite')
+    sc = Supercell(ex.lattice, [3, 2, 4], [1, 1, 1])
+    npc = sc.n_per_cell
+    for (x, y, z, b) in [(0, 0, 0, 0), (1, 0, 0, 5), (2, 1, 3, 29), (0, 1, 2, 12)]:
+        idx = ((x * 2 + y) * 4 + z) * npc + b
+        want = ex.lattice.cartesian_unit_cell_coords[b] + np.dot([x, y, z], ex.lattice.lattice_matrix)
+        assert np.allclose(sc.coordinates[idx], want, rtol=0, atol=1e-12)
+    fe = sc.element_sites(0)
+    assert len(fe) == 12 * 24 and fe[12] == npc
+    t = sc.site_centre_table(0)
+    assert t[npc + 3] == 12 + 3 and t[12] == -1
+
+
+def test_cell_geometry_matches_reference_formulas():
+    ex = H.load_example('hematite')
+    sc = ex.supercell
+    # size[0]==size[1] and block-diagonal lattice: row and column scaling agree
+    assert np.allclose(sc.translational_matrix, sc.cell_matrix)
+    ep = H.ewald_parameters(ex)
+    assert list(ep.k_max) == [10, 10, 16]
+    assert int(ep.num_k_vectors) == 7619
+    bvo = H.load_example('bvo')
+    assert list(H.ewald_parameters(bvo).k_max) == [9, 9, 10]
+
+
+def test_min_image_partial_pbc():
+    ex = H.load_example('hematite')
+    sc = Supercell(ex.lattice, [2, 2, 1], [1, 0, 1])
+    d = np.array([[30.0, 25.0, 40.0]])
+    out = sc.min_image(d)
+    f_in, f_out = d @ sc.cell_matrix_inv, out @ sc.cell_matrix_inv
+    assert abs(f_out[0, 1] - f_in[0, 1]) < 1e-12         # non-periodic axis untouched
+    assert abs(f_out[0, 0]) <= 0.5 + 1e-12 and abs(f_out[0, 2]) <= 0.5 + 1e-12
+
+
+@pytest.mark.parametrize('name', ['hematite', 'bvo'])
+def test_neighbour_tables_match_shipped_lists(name):
+    import warnings
+    ex = H.load_example(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        t = ex.supercell.hop_neighbor_tables()
+    for key, classes in ex.hop.items():
+        for ci, hops in enumerate(classes):
+            for hi, h in enumerate(hops):
+                mine = t[key][ci][hi]
+                assert np.array_equal(h.num_neighbors, mine.count)
+                for i, idx in enumerate(h.neighbor_system_element_indices):
+                    assert np.array_equal(np.asarray(idx), mine.index[i, :mine.count[i]])
+    if name == 'hematite':  # non-degenerate: vectors too (BVO 2x2x1 is degenerate)
+        h = ex.hop['Fe:Fe'][0][0]
+        vec = np.array([np.asarray(v) for v in h.displacement_vector_list])
+        assert np.abs(vec - t['Fe:Fe'][0][0].vector).max() < 1e-13
+
+
+def test_translation_path_equals_all_pairs():
+    ex = H.load_example('hematite')
+    sc = Supercell(ex.lattice, [5, 5, 2], [1, 1, 1])
+    a, b = sc.hop_neighbor_tables(), sc.hop_neighbor_tables(force_all_pairs=True)
+    for hi in range(2):
+        assert np.array_equal(a['Fe:Fe'][0][hi].index, b['Fe:Fe'][0][hi].index)
+        assert np.abs(a['Fe:Fe'][0][hi].vector - b['Fe:Fe'][0][hi].vector).max() < 1e-12
+
+
+def test_hop_list_roundtrip_in_reference_pickle_format(tmp_path):
+    ex = H.load_example('hematite')
+    t = ex.supercell.hop_neighbor_tables()
+    f = tmp_path / 'hop_neighbor_list.npy'
+    save_hop_neighbor_list(f, t)
+    raw = f.read_bytes()
+    assert b'PyCD.core' in raw and b'ReturnValues' in raw  # loadable by the reference
+    back = load_hop_neighbor_list(f)
+    h = back['Fe:Fe'][0][1]
+    assert np.array_equal(np.asarray(h.neighbor_system_element_indices[5]), t['Fe:Fe'][0][1].index[5, :1])
+    assert 'PyCD.core' not in sys.modules or hasattr(sys.modules['PyCD.core'], 'Material')
+    tab = HopTables(ex.lattice, ex.supercell, back, 'electron')
+    tab2 = HopTables(ex.lattice, ex.supercell, t, 'electron')
+    assert np.array_equal(tab.neigh, tab2.neigh) and np.array_equal(tab.hopvec, tab2.hopvec)
+
+
+def test_flat_tables():
+    ex = H.load_example('hematite')
+    tab = HopTables(ex.lattice, ex.supercell, ex.hop, 'electron')
+    assert tab.nn == 4 and tab.n_centres == 48 and tab.neigh.shape == (48, 4)
+    ev = constants.EV2HARTREE
+    assert np.allclose(tab.lam[0], np.array([1.74533] * 3 + [1.88683]) * ev)
+    assert np.allclose(tab.vab[0], np.array([0.184] * 3 + [0.028]) * ev)
+    assert np.all(np.diff(tab.neigh[:, :3], axis=1) > 0)  # ascending inside a hop distance
+    bvo = H.load_example('bvo')
+    tv = HopTables(bvo.lattice, bvo.supercell, bvo.hop, 'electron')
+    assert tv.nn == 6  # degenerate 2x2x1 cell
+    th = HopTables(bvo.lattice, bvo.supercell, bvo.hop, 'hole')
+    assert th.nn == 12 and th.n_class == 2 and th.n_centres == 64
+
+
+def test_run_parameters_and_initial_state():
+    ex, z = H.load_ref_case('bvo_2h')
+    run = H.run_parameters(ex)
+    assert run.species_type == 'hole' and run.q_carrier == 1.0 and run.n_proc == 24
+    assert set(np.round(run.e_rel / constants.EV2HARTREE, 4)) == {0.0, 0.0406}
+    assert run.n_path == int(run.t_final / run.time_interval) + 1
+    rng = H.rng_from_state_bytes(z['rnd_state_0'])
+    assert run.initial_occupancy_from(rng) == list(z['occ0'])
+    with pytest.raises(NotImplementedError):
+        H.run_parameters(H.load_example('bvo', species_count=[1, 1]))
+
+
+def test_preproduction_states_match_shipped_dump(tmp_path):
+    ex = H.load_example('hematite')
+    K.write_initial_rnd_states(tmp_path, 3, ex.sim['random_seed'])
+    mine = pickle.load(open(tmp_path / 'traj1' / 'initial_rnd_state.dump', 'rb'))
+    gold = pickle.load(open(ex.dir / 'traj1' / 'initial_rnd_state.dump', 'rb'))
+    assert mine == gold
+    assert (tmp_path / 'traj3' / 'initial_rnd_state.dump').exists()
+
+
+def test_precomputed_array_log_is_parseable_like_the_reference(tmp_path):
+    ex = H.load_example('hematite')
+    ep = H.ewald_parameters(ex)
+    from datetime import datetime
+    generate_report(datetime.now(), tmp_path, 'precomputed_array', 1, ''.join(log_prefix(ep)))
+    lines = open(tmp_path / 'precomputed_array.log').read().splitlines()
+    assert float(lines[3][7:16]) == 0.2667          # material_run.py:75-80
+    assert lines[3] == 'alpha: 2.667e-01 / angstrom (user-specified)'
+    assert lines[4] == 'r_cut: 4.618e+00 angstrom (user-specified)'
+    assert lines[5] == 'k_cut: 6.998e+00 / angstrom (user-specified)'
+    assert lines[6] == 'Real-space cutoff error: 2.406e+00'
+    assert lines[7] == 'Fourier-space cutoff error: 4.450e-76'
+    assert lines[9] == 'k_max: [10, 10, 16]' and lines[10] == 'number of k-vectors: 7619'
+    assert lines[-1].startswith('Time elapsed:  0 hours,  0 minutes')
+
+
+def test_ewald_parameter_searches_are_rejected():
+    ex = H.load_example('hematite')
+    with pytest.raises(NotImplementedError):
+        EwaldParameters(ex.supercell, 'optimal', 4.6, 7.0)
+
+
+def test_philox_initial_occupancy_is_sharding_invariant():
+    ex = H.load_example('hematite', species_count=[6, 0])
+    run = H.run_parameters(ex)
+    whole = K.philox_initial_occupancy(run.tables, 10, 6, seed=4)
+    part = K.philox_initial_occupancy(run.tables, 4, 6, seed=4, traj_id0=6)
+    assert np.array_equal(whole[6:], part)
+    assert all(len(set(r)) == 6 for r in whole)
+    assert np.all(run.tables.site_centre[whole] >= 0)
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    """nvcc cross-compiles for sm_100a without a GPU; every function declared in
+    include/pycd_b200.h is exported (no compute calls here)."""
+    path = nat.build()
+    lib = ctypes.CDLL(str(path))
+    header = (ROOT / 'include' / 'pycd_b200.h').read_text()
+    declared = set(re.findall(r'\b(pycd_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(nat.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pycd_abi_version() == 1
+    sass = subprocess.run(['cuobjdump', '-lelf', str(path)], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    with pytest.raises(nat.NativeError):
+        nat.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for f in (ROOT / 'pycd_b200').rglob('*.py'):
+        src = f.read_text()
+        assert 'import oracle' not in src and 'from oracle' not in src and 'ref_harness' not in src, f
+    for f in (ROOT / 'pycd_b200' / 'csrc').iterdir():
+        assert 'oracle' not in f.read_text().replace('oracle/pycd_oracle.c (tests', '').replace("oracle's order", ''), f
