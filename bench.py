@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--skip-msd', action='store_true')
+    ap.add_argument('--dense', action='store_true', help='step kernel gathers from the dense N x N array')
     return ap.parse_args()
 
 
@@ -253,7 +254,10 @@ def main():
                   'method': 'rows of unit cell 0 on the GPU + translation expansion of the rank\'s row block'}
 
     # ---- KMC system + ensemble -------------------------------------------------------
-    system = K.KmcSystem(ctx, run, P.data_ptr())
+    if args.dense:
+        system = K.KmcSystem(ctx, run, P.data_ptr())
+    else:
+        system = K.KmcSystem(ctx, run, p_unit.data_ptr(), layout='unit_rows')
     traj_id0 = rank * nt
     occ = K.philox_initial_occupancy(run.tables, nt, C_, seed, traj_id0=traj_id0)
     # time grid: ~1 row per 2 % of the timed KMC steps (k_total ~ C * 3.2e9 /s for Hematite e-)
@@ -382,7 +386,7 @@ def main():
             'config': {'workload': f'Hematite {args.size[0]}x{args.size[1]}x{args.size[2]} supercell '
                                    f'(N={N}), {C_} electrons, {nt} trajectories/GPU '
                                    f'({world * nt} total), Philox draws, fixed-step mode',
-                       'kmc_steps_per_step': S, 'n_proc': n_proc, 'refresh_interval': args.refresh,
+                       'kmc_steps_per_step': S, 'n_proc': n_proc, 'refresh_interval': args.refresh, 'p_layout': 'dense N x N' if args.dense else 'unit-cell rows (n_per_cell x N) + lattice translation',
                        'time_grid_rows': args.n_path,
                        'l2_policy': f'inputs larger than L2: precomputed array {N * N * 8 / 1e9:.1f} GB per GPU',
                        'parallelism': f'trajectories sharded over {world} GPU(s), no data-path collective'},

@@ -119,11 +119,19 @@ typedef struct {
     double vn;                  /* core.py:103 */
     double field[3];            /* core.py:1749-1761 */
     int32_t field_active;
+    int32_t p_layout;           /* PYCD_P_DENSE: P is (N,N).  PYCD_P_UNIT_ROWS: P is (n_basis,N) =
+                                   the rows of unit cell 0 (pycd_ewald_rows(0, n_basis)); elements are
+                                   addressed through lattice translation, pbc = [1,1,1] only */
+    int32_t n_basis;            /* UNIT_ROWS: sites per unit cell (<= 255) */
+    int32_t size[3];            /* UNIT_ROWS: supercell size (<= 255 per axis) */
 } pycd_kmc_system_desc;
+
+#define PYCD_P_DENSE 0
+#define PYCD_P_UNIT_ROWS 1
 
 int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc *desc, pycd_kmc_system **out);
 int pycd_kmc_system_destroy(pycd_kmc_system *sys);
-/* copy V_lat (N) back (tests) */
+/* copy V_lat back (tests): N values (dense) or n_basis values (unit rows) */
 int pycd_kmc_system_vlat(pycd_kmc_system *sys, double *v_lat);
 
 #define PYCD_RNG_REPLAY 0 /* u1,u2 pairs supplied by the host (the reference's random.random(), core.py:2799,2802) */
@@ -150,6 +158,9 @@ typedef struct {
 int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ensemble_desc *desc,
                              pycd_kmc_ensemble **out);
 int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens);
+/* Re-arm an ensemble (same sizes and run parameters) with new initial sites: t = 0, empty
+ * grid; avoids re-allocating the per-trajectory state between batches. */
+int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *occupancy0, uint64_t traj_id0);
 
 /* Advance every unfinished trajectory by at most max_steps KMC steps: rate evaluation
  * (core.py:1989-2050), selection + time advance + recording (core.py:2796-2861).

@@ -21,6 +21,7 @@ NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a',
 
 KC_EWALD_FOURIER, KC_EWALD_FINISH, KC_EWALD_EXPAND, KC_KMC_STEP, KC_MSD, KC_VLAT = range(6)
 RNG_REPLAY, RNG_PHILOX = 0, 1
+P_DENSE, P_UNIT_ROWS = 0, 1
 
 
 class NativeError(RuntimeError):
@@ -78,7 +79,8 @@ class KmcSystemDesc(C.Structure):
                 ('nn', C.c_int32), ('neigh', C.c_void_p), ('hopvec', C.c_void_p),
                 ('lam', C.c_void_p), ('vab', C.c_void_p), ('e_rel', C.c_void_p),
                 ('q_lat', C.c_void_p), ('q_carrier', C.c_double), ('kT', C.c_double),
-                ('vn', C.c_double), ('field', C.c_double * 3), ('field_active', C.c_int32)]
+                ('vn', C.c_double), ('field', C.c_double * 3), ('field_active', C.c_int32),
+                ('p_layout', C.c_int32), ('n_basis', C.c_int32), ('size', C.c_int32 * 3)]
 
 
 class KmcEnsembleDesc(C.Structure):
@@ -115,6 +117,7 @@ _SIGNATURES = {
     'pycd_kmc_ensemble_create': (C.c_int, [C.c_void_p, C.POINTER(KmcEnsembleDesc),
                                            C.POINTER(C.c_void_p)]),
     'pycd_kmc_ensemble_destroy': (C.c_int, [C.c_void_p]),
+    'pycd_kmc_ensemble_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     'pycd_kmc_advance': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.POINTER(C.c_int64)]),
     'pycd_kmc_read': (C.c_int, [C.c_void_p] + [C.c_void_p] * 8),

@@ -17,20 +17,22 @@
 namespace pycd {
 
 struct SysDev {
-    const double *P;
+    const double *P;          // dense: [N][N]; compact: [n_basis][N] (rows of unit cell 0)
     long long n_sites;
     const int *site_centre;
     const int *site_class;
+    const unsigned *site_pack;  // compact only: basis | x<<8 | y<<16 | z<<24
     int nn;
     const int *neigh;
     const double *hopvec;
     const double *lam;
     const double *vab;
     const double *e_rel;
-    const double *v_lat;
+    const double *v_lat;      // dense: [N]; compact: [n_basis]
     double qc, kT, vn;
     double field[3];
     int field_active;
+    int n_basis, sx, sy, sz;  // compact only
 };
 
 struct EnsDev {
@@ -68,7 +70,8 @@ struct AdvanceArgs {
     long long *steps_done; // [n_traj]
 };
 
-// Philox4x32-10; identical to oracle/pycd_oracle.c (tests/test_philox.py)
+// Philox4x32-10; identical to the CPU checker's generator (tests pin both to the
+// Random123 known-answer vector)
 __device__ __forceinline__ void philox_uniforms(unsigned long long seed, unsigned long long traj,
                                                 unsigned long long step, double &u1, double &u2)
 {
@@ -92,47 +95,131 @@ __device__ __forceinline__ void philox_uniforms(unsigned long long seed, unsigne
 
 constexpr double TIE_TOL = 1e-12;  // >> n_proc*eps: scan-order differences cannot cross it
 
+// A lattice site as the kernel carries it: index + (compact layout) packed cell/basis.
+struct Site {
+    int idx;
+    unsigned pack;
+};
+
+template <bool COMPACT>
+__device__ __forceinline__ Site make_site(const SysDev &S, int idx)
+{
+    Site s;
+    s.idx = idx;
+    s.pack = COMPACT ? __ldg(S.site_pack + idx) : 0u;
+    return s;
+}
+
+// P[x, y].  Dense: one 8-byte gather from the N x N array.  Compact: translation symmetry,
+// P[x,y] = Pu[basis_x][(cell_y - cell_x mod size)*n_basis + basis_y]; Pu (n_basis*N*8 bytes,
+// 7.2 MB at N = 30 000) stays L2-resident.
+template <bool COMPACT>
+__device__ __forceinline__ double ld_pair(const SysDev &S, const Site x, const Site y)
+{
+    if (!COMPACT) {
+        return __ldg(S.P + (long long)x.idx * S.n_sites + y.idx);
+    } else {
+        int dx = (int)((y.pack >> 8) & 255u) - (int)((x.pack >> 8) & 255u);
+        int dy = (int)((y.pack >> 16) & 255u) - (int)((x.pack >> 16) & 255u);
+        int dz = (int)(y.pack >> 24) - (int)(x.pack >> 24);
+        dx += dx < 0 ? S.sx : 0;
+        dy += dy < 0 ? S.sy : 0;
+        dz += dz < 0 ? S.sz : 0;
+        const int col = ((dx * S.sy + dy) * S.sz + dz) * S.n_basis + (int)(y.pack & 255u);
+        return __ldg(S.P + (long long)(x.pack & 255u) * S.n_sites + col);
+    }
+}
+
+template <bool COMPACT>
+__device__ __forceinline__ double ld_vlat(const SysDev &S, const Site x)
+{
+    return __ldg(S.v_lat + (COMPACT ? (int)(x.pack & 255u) : x.idx));
+}
+
 // Per-process cached quantities live in shared memory for the whole launch.
 struct ProcSmem {
     int *a, *b;                 // old / new site
+    unsigned *ap, *bp;          // packed (compact layout)
     double *t01, *t02, *shift;  // core.py:2004-2014, 2023-2025
     double *lam, *vab, *fs;     // lambda, V_AB, 0.5*E.hop
     double *k, *cum;
 };
 
-__device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ, int C, int p,
-                                               const double *fld, int field_active, ProcSmem &M)
+// everything of process p except the carrier sum (old/new site, self term, shift, lambda...)
+struct ProcStatic {
+    Site a, b;
+    double t02, shift, lam, vab, fs, vl;  // vl = V_lat[b] - V_lat[a]
+};
+
+template <bool COMPACT>
+__device__ __forceinline__ ProcStatic load_process_static(const SysDev &S, int slot, int a_idx,
+                                                          const double *fld, int field_active)
 {
-    const int c = p / S.nn, slot = p - c * S.nn;
-    const int a = s_occ[c];
-    const int e = S.site_centre[a];
-    const int b = S.neigh[(long long)e * S.nn + slot];
-    const int cls = S.site_class[a];
-    const double *Pa = S.P + (long long)a * S.n_sites, *Pb = S.P + (long long)b * S.n_sites;
-    // term01 in the oracle's order: start from the lattice part, add carriers in order
-    double t01 = __dsub_rn(S.v_lat[b], S.v_lat[a]);
-#pragma unroll 4
-    for (int c2 = 0; c2 < C; ++c2) {
-        const int sc = s_occ[c2];
-        t01 = __dadd_rn(t01, __dmul_rn(S.qc, __dsub_rn(__ldg(Pb + sc), __ldg(Pa + sc))));
-    }
-    M.a[p] = a;
-    M.b[p] = b;
-    M.t01[p] = t01;
-    M.t02[p] = __dmul_rn(S.qc, __dsub_rn(__ldg(Pa + a), __ldg(Pa + b)));
-    M.shift[p] = __dsub_rn(S.e_rel[b], S.e_rel[a]);
-    M.lam[p] = S.lam[cls * S.nn + slot];
-    M.vab[p] = S.vab[cls * S.nn + slot];
-    double fs = 0.0;
+    ProcStatic r;
+    const int e = __ldg(S.site_centre + a_idx);
+    const int b_idx = __ldg(S.neigh + (long long)e * S.nn + slot);
+    const int cls = __ldg(S.site_class + a_idx);
+    r.a = make_site<COMPACT>(S, a_idx);
+    r.b = make_site<COMPACT>(S, b_idx);
+    r.t02 = __dmul_rn(S.qc, __dsub_rn(ld_pair<COMPACT>(S, r.a, r.a), ld_pair<COMPACT>(S, r.a, r.b)));
+    r.shift = __dsub_rn(__ldg(S.e_rel + b_idx), __ldg(S.e_rel + a_idx));
+    r.lam = __ldg(S.lam + cls * S.nn + slot);
+    r.vab = __ldg(S.vab + cls * S.nn + slot);
+    r.fs = 0.0;
     if (field_active) {
         const double *hv = S.hopvec + ((long long)e * S.nn + slot) * 3;
-        fs = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(fld[0], hv[0]), __dmul_rn(fld[1], hv[1])),
-                                      __dmul_rn(fld[2], hv[2])));
+        r.fs = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(fld[0], hv[0]), __dmul_rn(fld[1], hv[1])),
+                                        __dmul_rn(fld[2], hv[2])));
     }
-    M.fs[p] = fs;
+    r.vl = __dsub_rn(ld_vlat<COMPACT>(S, r.b), ld_vlat<COMPACT>(S, r.a));
+    return r;
 }
 
-template <int BS>
+template <bool COMPACT>
+__device__ __forceinline__ void store_process_static(ProcSmem &M, int p, const ProcStatic &r)
+{
+    M.a[p] = r.a.idx;
+    M.b[p] = r.b.idx;
+    if (COMPACT) { M.ap[p] = r.a.pack; M.bp[p] = r.b.pack; }
+    M.t02[p] = r.t02;
+    M.shift[p] = r.shift;
+    M.lam[p] = r.lam;
+    M.vab[p] = r.vab;
+    M.fs[p] = r.fs;
+}
+
+// Full re-gather of one process by one thread, carriers in order (the checker's summation
+// order, so refresh_interval = 1 reproduces its rates bit for bit up to pow/log); loads are
+// issued in batches of GB pairs to keep 2*GB gathers in flight per thread.
+template <bool COMPACT>
+__device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ, const unsigned *s_occp,
+                                               int C, int p, const double *fld, int field_active,
+                                               ProcSmem &M)
+{
+    constexpr int GB = 8;
+    const ProcStatic ps = load_process_static<COMPACT>(S, p % S.nn, s_occ[p / S.nn], fld, field_active);
+    store_process_static<COMPACT>(M, p, ps);
+    const Site a = ps.a, b = ps.b;
+    double t01 = ps.vl;
+    for (int c0 = 0; c0 < C; c0 += GB) {
+        double pb[GB], pa[GB];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const int c2 = min(c0 + j, C - 1);
+            Site sc;
+            sc.idx = s_occ[c2];
+            sc.pack = COMPACT ? s_occp[c2] : 0u;
+            pb[j] = ld_pair<COMPACT>(S, b, sc);
+            pa[j] = ld_pair<COMPACT>(S, a, sc);
+        }
+#pragma unroll
+        for (int j = 0; j < GB; ++j)
+            if (c0 + j < C) t01 = __dadd_rn(t01, __dmul_rn(S.qc, __dsub_rn(pb[j], pa[j])));
+    }
+    M.t01[p] = t01;
+}
+
+template <int BS, bool COMPACT>
 __global__ void __launch_bounds__(BS)
 kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
 {
@@ -156,20 +243,26 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     double *s_disp = sd; sd += 3 * C;
     double *s_row = sd; sd += 3 * C;
     double *s_drift = sd; sd += 3 * C;
+    double *s_terms = sd; sd += nn * C;   // moved carrier: per (slot, carrier) contributions
     double *s_wsum = sd; sd += 32;
+    double *s_u = sd; sd += 2;            // this step's draws
     long long *s_ll = reinterpret_cast<long long *>(sd); sd += 2;  // rows [s_ll[0], s_ll[1]) pending
     int *si = reinterpret_cast<int *>(sd);
     M.a = si; si += n_proc;
     M.b = si; si += n_proc;
+    M.ap = reinterpret_cast<unsigned *>(si); si += n_proc;
+    M.bp = reinterpret_cast<unsigned *>(si); si += n_proc;
     int *s_occ = si; si += C;
-    int *s_flag = si; si += 2;      // [0] = selected process, [1] = trajectory finished
+    unsigned *s_occp = reinterpret_cast<unsigned *>(si); si += C;
+    int *s_wfirst = si; si += 32;   // per-warp first index with cum > u1
+    int *s_flag = si; si += 2;      // [0] = selected process (tie fallback), [1] = finished
 
     if (E.done[traj]) {
         if (tid == 0 && A.steps_done) A.steps_done[traj] = 0;
         return;
     }
 
-    double kT = E.kT_traj ? E.kT_traj[traj] : S.kT;
+    const double kT = E.kT_traj ? E.kT_traj[traj] : S.kT;
     double fld[3] = {S.field[0], S.field[1], S.field[2]};
     int field_active = S.field_active;
     if (E.field_traj) {
@@ -179,7 +272,11 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         field_active = (fld[0] != 0.0 || fld[1] != 0.0 || fld[2] != 0.0);
     }
 
-    for (int c = tid; c < C; c += BS) s_occ[c] = E.occ[(long long)traj * C + c];
+    for (int c = tid; c < C; c += BS) {
+        const int s = E.occ[(long long)traj * C + c];
+        s_occ[c] = s;
+        s_occp[c] = COMPACT ? S.site_pack[s] : 0u;
+    }
     for (int d = tid; d < 3 * C; d += BS) {
         s_disp[d] = E.disp[(long long)traj * 3 * C + d];
         s_row[d] = E.row[(long long)traj * 3 * C + d];
@@ -188,7 +285,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     // thread-0 scalars
     double t = E.t[traj];
     long long start = E.start_idx[traj];
-    long long steps_total = E.n_steps[traj];
+    const long long steps_total = E.n_steps[traj];
     long long n_tie = 0, n_clamp = 0;
     long long step_local = 0;
     const unsigned long long traj_gid = E.traj_id0 + (unsigned long long)traj;
@@ -214,78 +311,82 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             }
         }
         if (s_flag[1] || step_local >= A.max_steps) break;
-        __syncthreads();  // everyone has read s_ll / s_flag before thread 0 rewrites them
+        __syncthreads();  // (1) everyone has read s_ll / s_flag before thread 0 rewrites them
+
+        // ---- this step's uniform draws (thread 0; broadcast through shared memory) ----
+        if (tid == 0) {
+            double u1, u2;
+            if (E.rng_mode == PYCD_RNG_REPLAY) {
+                const double *dr = A.draws + ((long long)traj * A.max_steps + step_local) * 2;
+                u1 = dr[0];
+                u2 = dr[1];
+            } else {
+                philox_uniforms(E.seed, traj_gid, (unsigned long long)(steps_total + step_local), u1, u2);
+            }
+            s_u[0] = u1;
+            s_u[1] = u2;
+        }
 
         // ---- rates ----
         const bool full = (R <= 1) || ((steps_total + step_local) % R == 0);
-        double ksum = 0.0;
-        for (int p = tid; p < n_proc; p += BS) {
-            if (full) gather_process(S, s_occ, C, p, fld, field_active, M);
-            const double ew = __dmul_rn(__dmul_rn(2.0, S.qc), __dadd_rn(M.t01[p], M.t02[p]));  // core.py:2016
-            const double g0 = __dadd_rn(ew, M.shift[p]);
-            const double lam = M.lam[p];
-            const double lg = __dadd_rn(lam, g0);
-            const double gs = __dsub_rn(__dsub_rn(__ddiv_rn(__dmul_rn(lg, lg), __dmul_rn(4.0, lam)), M.vab[p]),
-                                        M.fs[p]);                                                // core.py:2045
-            const double kp = __dmul_rn(S.vn, pow(2.718281828459045, __ddiv_rn(-gs, kT)));        // core.py:2047
-            M.k[p] = kp;
-            ksum += kp;
-        }
-        // block sum (fixed tree order)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ksum += __shfl_xor_sync(0xffffffffu, ksum, o);
-        if (lane == 0) s_wsum[wid] = ksum;
-        __syncthreads();
+        double carry = 0.0;   // running prefix of raw rates over BS-sized groups
         double ktot = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) ktot += s_wsum[w];
-        __syncthreads();  // s_wsum reused by the scan
-
-        // ---- normalised inclusive scan, core.py:2797 ----
-        double carry = 0.0;
+        // pass 1: rates + inclusive scan of the raw rates (one BS-wide group at a time)
         for (int base = 0; base < n_proc; base += BS) {
             const int p = base + tid;
-            double x = (p < n_proc) ? __ddiv_rn(M.k[p], ktot) : 0.0;
+            double kp = 0.0;
+            if (p < n_proc) {
+                if (full) gather_process<COMPACT>(S, s_occ, s_occp, C, p, fld, field_active, M);
+                const double ew = __dmul_rn(__dmul_rn(2.0, S.qc), __dadd_rn(M.t01[p], M.t02[p]));  // core.py:2016
+                const double g0 = __dadd_rn(ew, M.shift[p]);
+                const double lam = M.lam[p];
+                const double lg = __dadd_rn(lam, g0);
+                const double gs = __dsub_rn(__dsub_rn(__ddiv_rn(__dmul_rn(lg, lg), __dmul_rn(4.0, lam)),
+                                                      M.vab[p]), M.fs[p]);                          // core.py:2045
+                kp = __dmul_rn(S.vn, pow(2.718281828459045, __ddiv_rn(-gs, kT)));                    // core.py:2047
+                M.k[p] = kp;
+            }
+            double x = kp;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const double y = __shfl_up_sync(0xffffffffu, x, o);
                 if (lane >= o) x += y;
             }
             if (lane == 31) s_wsum[wid] = x;
-            __syncthreads();
-            double pre = carry;
-            for (int w = 0; w < wid; ++w) pre += s_wsum[w];
-            if (p < n_proc) M.cum[p] = pre + x;
-            double tot = carry;
-            for (int w = 0; w < NW; ++w) tot += s_wsum[w];
+            __syncthreads();  // (2)
+            double pre = carry, tot = carry;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const double v = s_wsum[w];
+                if (w < wid) pre += v;
+                tot += v;
+            }
+            if (p < n_proc) M.cum[p] = pre + x;   // un-normalised inclusive prefix
             carry = tot;
-            __syncthreads();
+            if (base + BS < n_proc) __syncthreads();  // s_wsum reused by the next group
         }
+        ktot = carry;
+        const double u1 = s_u[0], u2 = s_u[1];
 
-        // ---- uniform draws ----
-        double u1, u2;
-        if (E.rng_mode == PYCD_RNG_REPLAY) {
-            const double *dr = A.draws + ((long long)traj * A.max_steps + step_local) * 2;
-            u1 = dr[0];
-            u2 = dr[1];
-        } else {
-            philox_uniforms(E.seed, traj_gid, (unsigned long long)(steps_total + step_local), u1, u2);
+        // ---- first index with cumsum(k/k_total) > u1, core.py:2797-2800 ----
+        int first = INT_MAX;
+        for (int base = 0; base < n_proc; base += BS) {
+            const int p = base + tid;
+            const bool hit = (p < n_proc) && (__ddiv_rn(M.cum[p], ktot) > u1);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m && first == INT_MAX) first = base + wid * 32 + (__ffs(m) - 1);
         }
-
-        // ---- first index with cum > u1, core.py:2800 ----
-        if (tid == 0) s_flag[0] = INT_MAX;
-        __syncthreads();
-        for (int p = tid; p < n_proc; p += BS)
-            if (M.cum[p] > u1 && (p == 0 || !(M.cum[p - 1] > u1))) atomicMin(&s_flag[0], p);
-        __syncthreads();
-        int sel = s_flag[0];
+        if (lane == 0) s_wfirst[wid] = first;
+        __syncthreads();  // (3) M.cum, s_wfirst visible
+        int sel = INT_MAX;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sel = min(sel, s_wfirst[w]);
         bool tie = (sel == INT_MAX);
         if (!tie) {
-            const double hi = M.cum[sel], lo = sel > 0 ? M.cum[sel - 1] : 0.0;
+            const double hi = M.cum[sel] / ktot, lo = sel > 0 ? M.cum[sel - 1] / ktot : 0.0;
             tie = (hi - u1 < TIE_TOL) || (sel > 0 && u1 - lo < TIE_TOL);
         }
-        if (tie) {  // block-uniform branch: redo the selection in the reference's sequential order
-            __syncthreads();
+        if (tie) {  // block-uniform: redo the selection in the reference's sequential order
             if (tid == 0) {
                 double kseq = 0.0;
                 for (int p = 0; p < n_proc; ++p) kseq += M.k[p];
@@ -295,7 +396,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                     cum += M.k[p] / kseq;
                     if (cum > u1) { s2 = p; break; }
                 }
-                if (s2 < 0) { s2 = n_proc - 1; ++n_clamp; }  // reference raises IndexError here
+                if (s2 < 0) { s2 = n_proc - 1; ++n_clamp; }  // the reference raises IndexError here
                 ++n_tie;
                 s_flag[0] = s2;
             }
@@ -304,27 +405,54 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         }
 
         const int cs = sel / nn, slot = sel - cs * nn;
-        const int a_old = M.a[sel], b_new = M.b[sel];
+        Site a_old, b_new;
+        a_old.idx = M.a[sel];
+        b_new.idx = M.b[sel];
+        a_old.pack = COMPACT ? M.ap[sel] : 0u;
+        b_new.pack = COMPACT ? M.bp[sel] : 0u;
         const bool next_full = (R <= 1) || ((steps_total + step_local + 1) % R == 0);
 
-        // ---- issue the cache patches first (long-latency gathers) ----
+        // ---- issue the long-latency gathers of the incremental update first ----
+        // (a) untouched processes: 4 elements each
         double patch[4];
         int npatch = 0;
         if (!next_full) {
             for (int p = tid; p < n_proc && npatch < 4; p += BS) {
-                if (p / nn == cs) { patch[npatch++] = 0.0; continue; }
-                const long long ra = (long long)M.a[p] * S.n_sites, rb = (long long)M.b[p] * S.n_sites;
-                const double nb_ = __ldg(S.P + rb + b_new), na_ = __ldg(S.P + ra + b_new);
-                const double ob_ = __ldg(S.P + rb + a_old), oa_ = __ldg(S.P + ra + a_old);
-                patch[npatch++] = S.qc * (nb_ - na_) - S.qc * (ob_ - oa_);
+                double v = 0.0;
+                if (p / nn != cs) {
+                    Site pa, pb;
+                    pa.idx = M.a[p]; pb.idx = M.b[p];
+                    pa.pack = COMPACT ? M.ap[p] : 0u;
+                    pb.pack = COMPACT ? M.bp[p] : 0u;
+                    const double nb_ = ld_pair<COMPACT>(S, pb, b_new), na_ = ld_pair<COMPACT>(S, pa, b_new);
+                    const double ob_ = ld_pair<COMPACT>(S, pb, a_old), oa_ = ld_pair<COMPACT>(S, pa, a_old);
+                    v = S.qc * (nb_ - na_) - S.qc * (ob_ - oa_);
+                }
+                patch[npatch++] = v;
+            }
+            // (b) the moved carrier's nn processes: (slot, carrier) items over the whole block
+            const int e_new = __ldg(S.site_centre + b_new.idx);
+            for (int item = tid; item < nn * C; item += BS) {
+                const int sl = item / C, c2 = item - sl * C;
+                const Site nbr = make_site<COMPACT>(S, __ldg(S.neigh + (long long)e_new * nn + sl));
+                Site sc;
+                if (c2 == cs) sc = b_new;
+                else { sc.idx = s_occ[c2]; sc.pack = COMPACT ? s_occp[c2] : 0u; }
+                s_terms[item] = S.qc * (ld_pair<COMPACT>(S, nbr, sc) - ld_pair<COMPACT>(S, b_new, sc));
             }
         }
+
+        // (c) static parts of the moved carrier's new processes: lane j of warp w <-> slot w + j*NW
+        ProcStatic moved;
+        const int my_slot = wid + lane * NW;
+        const bool has_slot = !next_full && my_slot < nn;
+        if (has_slot) moved = load_process_static<COMPACT>(S, my_slot, b_new.idx, fld, field_active);
 
         // ---- thread 0: time advance + bookkeeping, core.py:2802-2830, 2844-2861 ----
         if (tid == 0) {
             t -= log(u2) / ktot;
             const long long end = (long long)(t / E.dt_grid);
-            const int e = S.site_centre[a_old];
+            const int e = S.site_centre[a_old.idx];
             const double *hv = S.hopvec + ((long long)e * nn + slot) * 3;
             const double kp = M.k[sel];
 #pragma unroll
@@ -346,27 +474,43 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             s_ll[0] = r0;
             s_ll[1] = r1;
             s_flag[1] = fin;
+            s_occ[cs] = b_new.idx;
+            if (COMPACT) s_occp[cs] = b_new.pack;
         }
-        if (tid == 0) s_occ[cs] = b_new;
-        __syncthreads();  // s_occ, s_ll, s_flag visible
+        __syncthreads();  // (4) s_terms, s_occ, s_ll, s_flag visible
 
         // ---- bring the cached sums up to date for the next step ----
         if (!next_full) {
             int ip = 0;
             for (int p = tid; p < n_proc; p += BS, ++ip) {
-                if (p / nn == cs) {
-                    gather_process(S, s_occ, C, p, fld, field_active, M);
-                } else if (ip < 4) {
+                if (p / nn == cs) continue;
+                if (ip < 4) {
                     M.t01[p] += patch[ip];
                 } else {
-                    const long long ra = (long long)M.a[p] * S.n_sites, rb = (long long)M.b[p] * S.n_sites;
-                    M.t01[p] += S.qc * (__ldg(S.P + rb + b_new) - __ldg(S.P + ra + b_new)) -
-                                S.qc * (__ldg(S.P + rb + a_old) - __ldg(S.P + ra + a_old));
+                    Site pa, pb;
+                    pa.idx = M.a[p]; pb.idx = M.b[p];
+                    pa.pack = COMPACT ? M.ap[p] : 0u;
+                    pb.pack = COMPACT ? M.bp[p] : 0u;
+                    M.t01[p] += S.qc * (ld_pair<COMPACT>(S, pb, b_new) - ld_pair<COMPACT>(S, pa, b_new)) -
+                                S.qc * (ld_pair<COMPACT>(S, pb, a_old) - ld_pair<COMPACT>(S, pa, a_old));
+                }
+            }
+            // one warp per slot of the moved carrier: reduce its C contributions
+            int j = 0;
+            for (int sl = wid; sl < nn; sl += NW, ++j) {
+                double acc = 0.0;
+                for (int c2 = lane; c2 < C; c2 += 32) acc += s_terms[sl * C + c2];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == j) {
+                    const int p = cs * nn + sl;
+                    store_process_static<COMPACT>(M, p, moved);
+                    M.t01[p] = moved.vl + acc;
                 }
             }
         }
         ++step_local;
-        __syncthreads();
+        __syncthreads();  // (5)
     }
 
     // ---- write the state back ----
@@ -393,12 +537,12 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
 // V_lat = P . q_lat, one warp per row, double-double accumulation so that the
 // differences V_lat[b]-V_lat[a] keep ~1e-16 Ha accuracy at N = 30 000.
 __global__ void __launch_bounds__(256)
-vlat_kernel(const double *__restrict__ P, const double *__restrict__ q, long long n,
+vlat_kernel(const double *__restrict__ P, const double *__restrict__ q, long long n_rows, long long n,
             double *__restrict__ v)
 {
     const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (row >= n) return;
+    if (row >= n_rows) return;
     const double *pr = P + row * n;
     double hi = 0.0, lo = 0.0;
     for (long long j = lane; j < n; j += 32) {
@@ -420,10 +564,20 @@ vlat_kernel(const double *__restrict__ P, const double *__restrict__ q, long lon
     if (lane == 0) v[row] = hi + lo;
 }
 
-static size_t kmc_smem_bytes(int n_proc, int C) {
-    const size_t doubles = (size_t)8 * n_proc + (size_t)9 * C + 32 + 2;
-    const size_t ints = (size_t)2 * n_proc + C + 2;
+static size_t kmc_smem_bytes(int n_proc, int C, int nn) {
+    const size_t doubles = (size_t)8 * n_proc + (size_t)9 * C + (size_t)nn * C + 32 + 2 + 2;
+    const size_t ints = (size_t)4 * n_proc + 2 * (size_t)C + 32 + 2;
     return doubles * 8 + ((ints + 1) / 2) * 8;
+}
+
+// basis | x<<8 | y<<16 | z<<24 per site (site = cell*n_basis + basis, cell = (x*sy + y)*sz + z)
+__global__ void site_pack_kernel(unsigned *out, long long n, int nb, int sy, int sz)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cell = (int)(i / nb), b = (int)(i - (long long)cell * nb);
+    const int z = cell % sz, y = (cell / sz) % sy, x = cell / (sz * sy);
+    out[i] = (unsigned)b | ((unsigned)x << 8) | ((unsigned)y << 16) | ((unsigned)z << 24);
 }
 
 }  // namespace pycd
@@ -439,6 +593,8 @@ struct pycd_kmc_system {
     InBuf<int> site_centre, site_class, neigh;
     InBuf<double> hopvec, lam, vab, e_rel;
     DevBuf<double> v_lat;
+    DevBuf<unsigned> site_pack;
+    bool compact = false;
 };
 
 struct pycd_kmc_ensemble {
@@ -465,7 +621,23 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             sys->ctx = ctx;
             const size_t n = (size_t)d->n_sites;
             cudaStream_t s = ctx->stream;
-            sys->P.bind(d->P, n * n, s);
+            sys->compact = (d->p_layout == PYCD_P_UNIT_ROWS);
+            size_t p_rows = n;
+            if (sys->compact) {
+                const long long cells = (long long)d->size[0] * d->size[1] * d->size[2];
+                PYCD_REQUIRE(d->n_basis > 0 && d->n_basis <= 255, "compact layout needs 1..255 sites per unit cell");
+                PYCD_REQUIRE(d->size[0] > 0 && d->size[0] <= 255 && d->size[1] > 0 && d->size[1] <= 255 &&
+                                 d->size[2] > 0 && d->size[2] <= 255, "compact layout needs 1..255 cells per axis");
+                PYCD_REQUIRE(cells * d->n_basis == d->n_sites, "n_basis * cells != n_sites");
+                p_rows = (size_t)d->n_basis;
+                sys->site_pack.alloc(n);
+                site_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sys->site_pack.p, (long long)n,
+                                                                             d->n_basis, d->size[1], d->size[2]);
+                check_launch(ctx, "site_pack_kernel");
+            } else {
+                PYCD_REQUIRE(d->p_layout == PYCD_P_DENSE, "unknown p_layout");
+            }
+            sys->P.bind(d->P, p_rows * n, s);
             sys->site_centre.bind(d->site_centre, n, s);
             sys->site_class.bind(d->site_class, n, s);
             sys->neigh.bind(d->neigh, (size_t)d->n_centres * d->nn, s);
@@ -475,10 +647,12 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             sys->e_rel.bind(d->e_rel, n, s);
             InBuf<double> q;
             q.bind(d->q_lat, n, s);
-            sys->v_lat.alloc(n);
+            // V_lat = P . q_lat: one entry per site (dense) or per basis site (compact: the
+            // lattice charges are periodic, so V_lat[i] = V_lat[basis_i])
+            sys->v_lat.alloc(p_rows);
             KernelTimer tv(ctx, KC_VLAT);
-            vlat_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(sys->P.p, q.p, (long long)n,
-                                                                         sys->v_lat.p);
+            vlat_kernel<<<(unsigned)((p_rows * 32 + 255) / 256), 256, 0, s>>>(sys->P.p, q.p, (long long)p_rows,
+                                                                              (long long)n, sys->v_lat.p);
             check_launch(ctx, "vlat_kernel");
             tv.stop(1);
             PYCD_CUDA(cudaStreamSynchronize(s));
@@ -491,6 +665,8 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             v.qc = d->q_carrier; v.kT = d->kT; v.vn = d->vn;
             for (int k = 0; k < 3; ++k) v.field[k] = d->field[k];
             v.field_active = d->field_active;
+            v.site_pack = sys->site_pack.p;
+            v.n_basis = d->n_basis; v.sx = d->size[0]; v.sy = d->size[1]; v.sz = d->size[2];
             sys->n_centres = d->n_centres;
             sys->n_class = d->n_class;
         } catch (...) {
@@ -513,7 +689,7 @@ extern "C" int pycd_kmc_system_vlat(pycd_kmc_system *sys, double *v_lat) {
     return guarded([&] {
         PYCD_REQUIRE(sys && v_lat, "NULL argument");
         DeviceGuard g(sys->ctx);
-        PYCD_CUDA(cudaMemcpy(v_lat, sys->v_lat.p, sizeof(double) * sys->dev.n_sites,
+        PYCD_CUDA(cudaMemcpy(v_lat, sys->v_lat.p, sizeof(double) * sys->v_lat.n,
                              is_device_pointer(v_lat) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
     });
 }
@@ -591,6 +767,25 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
     });
 }
 
+extern "C" int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *occupancy0, uint64_t traj_id0) {
+    return guarded([&] {
+        PYCD_REQUIRE(ens && occupancy0, "NULL argument");
+        pycd_ctx *ctx = ens->sys->ctx;
+        DeviceGuard g(ctx);
+        EnsDev &E = ens->dev;
+        const size_t nt = (size_t)E.n_traj;
+        cudaStream_t s = ctx->stream;
+        PYCD_CUDA(cudaMemcpyAsync(ens->occ.p, occupancy0, sizeof(int) * nt * E.C, cudaMemcpyDefault, s));
+        ens->done.zero(s); ens->t.zero(s); ens->disp.zero(s); ens->row.zero(s); ens->drift.zero(s);
+        ens->rates.zero(s); ens->n_steps.zero(s); ens->near_tie.zero(s); ens->clamped.zero(s);
+        ens->unwrapped.zero(s);
+        std::vector<long long> ones(nt, 1);
+        PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
+        E.traj_id0 = traj_id0;
+        PYCD_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 extern "C" int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens) {
     return guarded([&] {
         if (!ens) return;
@@ -599,13 +794,20 @@ extern "C" int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens) {
     });
 }
 
-template <int BS>
-static void launch_step(pycd_ctx *ctx, const SysDev &S, const EnsDev &E, const AdvanceArgs &A, size_t smem) {
-    auto kern = kmc_step_kernel<BS>;
+template <int BS, bool COMPACT>
+static void launch_step_impl(pycd_ctx *ctx, const SysDev &S, const EnsDev &E, const AdvanceArgs &A, size_t smem) {
+    auto kern = kmc_step_kernel<BS, COMPACT>;
     if (smem > 48 * 1024)
         PYCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)E.n_traj, BS, smem, ctx->stream>>>(S, E, A);
     check_launch(ctx, "kmc_step_kernel");
+}
+
+template <int BS>
+static void launch_step(pycd_ctx *ctx, bool compact, const SysDev &S, const EnsDev &E, const AdvanceArgs &A,
+                        size_t smem) {
+    if (compact) launch_step_impl<BS, true>(ctx, S, E, A, smem);
+    else launch_step_impl<BS, false>(ctx, S, E, A, smem);
 }
 
 extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
@@ -638,13 +840,14 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         A.events_out = ev.dev();
         A.times_out = tm.dev();
         A.steps_done = sdn.dev();
-        const size_t smem = kmc_smem_bytes(E.n_proc, E.C);
+        const size_t smem = kmc_smem_bytes(E.n_proc, E.C, ens->sys->dev.nn);
         PYCD_REQUIRE(smem <= 200 * 1024, "trajectory state does not fit in shared memory");
+        const bool cp = ens->sys->compact;
         KernelTimer tk(ctx, KC_KMC_STEP);
-        if (E.n_proc <= 32) launch_step<32>(ctx, ens->sys->dev, E, A, smem);
-        else if (E.n_proc <= 64) launch_step<64>(ctx, ens->sys->dev, E, A, smem);
-        else if (E.n_proc <= 128) launch_step<128>(ctx, ens->sys->dev, E, A, smem);
-        else launch_step<256>(ctx, ens->sys->dev, E, A, smem);
+        if (E.n_proc <= 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (E.n_proc <= 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (E.n_proc <= 128) launch_step<128>(ctx, cp, ens->sys->dev, E, A, smem);
+        else launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
         tk.stop(1);
         ev.finish(s);
         tm.finish(s);

@@ -124,10 +124,21 @@ def philox_initial_occupancy(tables, n_traj, n_carriers, seed, traj_id0=0):
 
 class KmcSystem:
     """Device-resident static tables (pycd_kmc_system).  P may be a numpy array (copied
-    to the device) or a torch CUDA tensor / device address (used in place)."""
+    to the device) or a torch CUDA tensor / device address (used in place).
 
-    def __init__(self, ctx, run, P, kT=None, field=None):
+    layout='dense': P is the full (N, N) array.  layout='unit_rows': P is (n_per_cell, N),
+    the rows of unit cell 0 (ewald_rows(0, n_per_cell)); every element is reached through
+    lattice translation, which needs pbc = [1, 1, 1]; the 7.2 MB table of the 10x10x10
+    Hematite cell stays L2-resident instead of gathering from a 7.2 GB array."""
+
+    def __init__(self, ctx, run, P, kT=None, field=None, layout='dense'):
         t = run.tables
+        sc = run.supercell
+        if layout not in ('dense', 'unit_rows'):
+            raise ValueError("layout must be 'dense' or 'unit_rows'")
+        if layout == 'unit_rows' and not bool(np.all(sc.pbc == 1)):
+            raise ValueError("layout='unit_rows' needs pbc = [1, 1, 1]")
+        self.layout = layout
         self.ctx, self.run = ctx, run
         self._keep = dict(
             site_centre=np.ascontiguousarray(t.site_centre, dtype=np.int32),
@@ -140,9 +151,10 @@ class KmcSystem:
             q_lat=np.ascontiguousarray(run.q_lat, dtype=np.float64))
         if isinstance(P, np.ndarray):
             P = np.ascontiguousarray(P, dtype=np.float64)
-            n = run.supercell.num_system_elements
-            if P.shape != (n, n):
-                raise ValueError(f'precomputed array has shape {P.shape}, expected {(n, n)}')
+            n = sc.num_system_elements
+            want = (n, n) if layout == 'dense' else (sc.n_per_cell, n)
+            if P.shape != want:
+                raise ValueError(f'precomputed array has shape {P.shape}, expected {want}')
         self._P = P
         d = nat.KmcSystemDesc()
         d.n_sites = run.supercell.num_system_elements
@@ -158,6 +170,9 @@ class KmcSystem:
         f = run.field if field is None else np.asarray(field, dtype=float)
         d.field[:] = [float(x) for x in f]
         d.field_active = int(run.field_active if field is None else bool(np.any(f != 0)))
+        d.p_layout = nat.P_UNIT_ROWS if layout == 'unit_rows' else nat.P_DENSE
+        d.n_basis = int(sc.n_per_cell)
+        d.size[:] = [int(v) for v in sc.system_size]
         self._h = C.c_void_p()
         nat.check(nat.lib().pycd_kmc_system_create(ctx.handle, C.byref(d), C.byref(self._h)))
 
@@ -168,7 +183,8 @@ class KmcSystem:
         return self._h
 
     def v_lat(self):
-        out = np.empty(self.run.supercell.num_system_elements)
+        sc = self.run.supercell
+        out = np.empty(sc.num_system_elements if self.layout == 'dense' else sc.n_per_cell)
         nat.check(nat.lib().pycd_kmc_system_vlat(self.handle, nat.ptr(out)))
         return out
 
@@ -232,6 +248,13 @@ class KmcEnsemble:
         if not self._h:
             raise nat.NativeError('KMC ensemble already destroyed')
         return self._h
+
+    def reset(self, occupancy0, traj_id0=0):
+        """Re-arm with new initial sites (t = 0, empty grid) without re-allocating."""
+        occ = np.ascontiguousarray(occupancy0, dtype=np.int32)
+        if occ.shape != (self.n_traj, self.n_carriers):
+            raise ValueError(f'occupancy must have shape {(self.n_traj, self.n_carriers)}')
+        nat.check(nat.lib().pycd_kmc_ensemble_reset(self.handle, nat.ptr(occ), int(traj_id0)))
 
     def advance(self, max_steps, draws=None, want_events=False, want_times=False):
         """At most max_steps KMC steps per unfinished trajectory.  Returns a dict with

@@ -164,6 +164,52 @@ def test_philox_ensemble_matches_oracle(ctx, refresh):
     assert np.array_equal(got['unwrapped'], ref['unwrapped'])
 
 
+@pytest.mark.parametrize('refresh', [1, 16])
+@pytest.mark.parametrize('case', ['hematite_3x3x2_12e', 'bvo_3x3x1_6h'])
+def test_unit_rows_layout_matches_oracle_on_expanded_array(ctx, case, refresh):
+    """Translation-symmetric table: the GPU gathers from the (n_per_cell, N) rows of unit
+    cell 0; the oracle runs on the expanded dense (N, N) array.  Fresh geometry, Ewald
+    array computed on the GPU."""
+    from pycd_b200.kmc import RunParameters
+    from pycd_b200.lattice import Supercell
+    name, size, species = {'hematite_3x3x2_12e': ('hematite', [3, 3, 2], [12, 0]),
+                           'bvo_3x3x1_6h': ('bvo', [3, 3, 1], [0, 6])}[case]
+    ex = H.load_example(name)
+    sim = ex.sim
+    sc = Supercell(ex.lattice, size, [1, 1, 1])
+    run = RunParameters(ex.lattice, sc, sc.hop_neighbor_tables(), sim['temp'], 'full', 'full',
+                        sim['t_final'], sim['time_interval'], species, {}, sim['relative_energies'],
+                        sim['external_field'])
+    ep = EW.EwaldParameters(sc, ex.cfg['alpha'], ex.cfg['r_cut'], ex.cfg['k_cut'])
+    coords = np.ascontiguousarray(sc.coordinates)
+    p_unit, _ = EW.ewald_rows(ctx, ep, coords, 0, sc.n_per_cell)
+    dense = EW.ewald_expand(ctx, sc, p_unit, 0, sc.num_system_elements)
+    direct, _ = EW.ewald_rows(ctx, ep, coords, 0, sc.num_system_elements)
+    assert np.abs(dense - direct).max() <= 1e-13 * np.abs(direct).max()  # translation invariance
+    n_traj, steps = 16, 2000
+    occ = K.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed=21)
+    kw = dict(dt_grid=run.time_interval / 500, n_path=128, step_limit=steps, stop_at_grid_end=False)
+    system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=21, refresh_interval=refresh, **kw)
+    while ens.advance_resident(400) > 0:
+        pass
+    got = ens.read()
+    # re-armed ensemble reproduces itself
+    ens.reset(occ)
+    while ens.advance_resident(2000) > 0:
+        pass
+    again = ens.read()
+    ens.close()
+    vl = system.v_lat()
+    system.close()
+    ref = O.KmcOracle(run, dense, rng_mode=1, seed=21, **kw).ensemble(occ)
+    assert np.allclose(vl, O.vlat(dense, run.q_lat)[:sc.n_per_cell], rtol=0, atol=1e-14)
+    assert np.array_equal(got['n_steps'], ref['n_steps'])
+    assert np.array_equal(got['occupancy'], ref['occupancy'])
+    assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+    assert np.array_equal(again['unwrapped'], got['unwrapped'])
+
+
 def test_sharding_is_invisible(ctx):
     """Trajectories keyed by global id: running [0,32) and [32,64) separately equals [0,64)."""
     ex, run = _philox_case(species=(4, 0))
