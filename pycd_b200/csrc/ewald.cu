@@ -353,9 +353,18 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
                                       cudaMemcpyHostToDevice, ctx->stream));
             const long long bm = wide ? 128 : 32, bn = wide ? 128 : 256;
             const long long tiles = ((n_rows + bm - 1) / bm) * ((n + bn - 1) / bn);
-            long long want = (2ll * ctx->n_sm + tiles - 1) / tiles;
-            const long long ws_cap = (1ll << 30) / (n_rows * n * 8) > 0 ? (1ll << 30) / (n_rows * n * 8) : 1;
-            k_split = (int)std::max(1ll, std::min({want, (long long)n_chunks, ws_cap}));
+            // split-k so that the grid fills whole waves of the SMs (1 CTA/SM): among the
+            // candidates pick the best-filled last wave, preferring fewer splits on ties
+            const long long ws_cap = std::max(1ll, (1ll << 30) / (n_rows * n * 8));
+            const long long ks_max = std::min({(long long)n_chunks, ws_cap, 32ll});
+            double best_fill = -1.0;
+            for (long long ks = 1; ks <= ks_max; ++ks) {
+                const long long grid = tiles * ks;
+                const long long waves = (grid + ctx->n_sm - 1) / ctx->n_sm;
+                double fill = (double)grid / (double)(waves * ctx->n_sm);
+                if (grid < ctx->n_sm) fill = (double)grid / ctx->n_sm;
+                if (fill > best_fill + 0.02) { best_fill = fill; k_split = (int)ks; }
+            }
         }
         DevBuf<double> ws;
         double *partials = o.dev();

@@ -24,6 +24,7 @@ struct SysDev {
     const unsigned *site_pack;  // compact only: basis | x<<8 | y<<16 | z<<24
     int nn;
     const int *neigh;
+    const unsigned *neigh_pack; // compact only: site_pack of neigh[e][slot]
     const double *hopvec;
     const double *lam;
     const double *vab;
@@ -136,42 +137,54 @@ __device__ __forceinline__ double ld_vlat(const SysDev &S, const Site x)
     return __ldg(S.v_lat + (COMPACT ? (int)(x.pack & 255u) : x.idx));
 }
 
+// np.e ** y  (core.py:2047).  The reference raises the ROUNDED constant np.e =
+// 2.718281828459045 to the power y, i.e. exp(y * ln(np.e)) with ln(np.e) = 1 - 5.318e-17;
+// a pow() call would recompute that logarithm for every rate.
+__device__ __forceinline__ double pow_np_e(double y)
+{
+    const double e = exp(y);
+    return fma(e, y * -5.318237706605891e-17, e);
+}
+
 // Per-process cached quantities live in shared memory for the whole launch.
 struct ProcSmem {
-    int *a, *b;                 // old / new site
-    unsigned *ap, *bp;          // packed (compact layout)
+    int *a, *b, *be;            // old site, new site, centre index of the new site
+    unsigned *ap, *bp;          // packed cell/basis (compact layout)
     double *t01, *t02, *shift;  // core.py:2004-2014, 2023-2025
     double *lam, *vab, *fs;     // lambda, V_AB, 0.5*E.hop
     double *k, *cum;
 };
 
-// everything of process p except the carrier sum (old/new site, self term, shift, lambda...)
+// everything of a process except the carrier sum (new site, self term, shift, lambda...)
 struct ProcStatic {
     Site a, b;
+    int be;
     double t02, shift, lam, vab, fs, vl;  // vl = V_lat[b] - V_lat[a]
 };
 
+// a = current site of the carrier (index, pack, centre index e known to the caller)
 template <bool COMPACT>
-__device__ __forceinline__ ProcStatic load_process_static(const SysDev &S, int slot, int a_idx,
+__device__ __forceinline__ ProcStatic load_process_static(const SysDev &S, int slot, Site a, int e,
                                                           const double *fld, int field_active)
 {
     ProcStatic r;
-    const int e = __ldg(S.site_centre + a_idx);
-    const int b_idx = __ldg(S.neigh + (long long)e * S.nn + slot);
-    const int cls = __ldg(S.site_class + a_idx);
-    r.a = make_site<COMPACT>(S, a_idx);
-    r.b = make_site<COMPACT>(S, b_idx);
-    r.t02 = __dmul_rn(S.qc, __dsub_rn(ld_pair<COMPACT>(S, r.a, r.a), ld_pair<COMPACT>(S, r.a, r.b)));
-    r.shift = __dsub_rn(__ldg(S.e_rel + b_idx), __ldg(S.e_rel + a_idx));
+    const long long ns = (long long)e * S.nn + slot;
+    r.a = a;
+    r.b.idx = __ldg(S.neigh + ns);
+    r.b.pack = COMPACT ? __ldg(S.neigh_pack + ns) : 0u;
+    const int cls = __ldg(S.site_class + a.idx);
+    r.be = __ldg(S.site_centre + r.b.idx);
+    r.t02 = __dmul_rn(S.qc, __dsub_rn(ld_pair<COMPACT>(S, a, a), ld_pair<COMPACT>(S, a, r.b)));
+    r.shift = __dsub_rn(__ldg(S.e_rel + r.b.idx), __ldg(S.e_rel + a.idx));
     r.lam = __ldg(S.lam + cls * S.nn + slot);
     r.vab = __ldg(S.vab + cls * S.nn + slot);
     r.fs = 0.0;
     if (field_active) {
-        const double *hv = S.hopvec + ((long long)e * S.nn + slot) * 3;
+        const double *hv = S.hopvec + ns * 3;
         r.fs = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(fld[0], hv[0]), __dmul_rn(fld[1], hv[1])),
                                         __dmul_rn(fld[2], hv[2])));
     }
-    r.vl = __dsub_rn(ld_vlat<COMPACT>(S, r.b), ld_vlat<COMPACT>(S, r.a));
+    r.vl = __dsub_rn(ld_vlat<COMPACT>(S, r.b), ld_vlat<COMPACT>(S, a));
     return r;
 }
 
@@ -180,6 +193,7 @@ __device__ __forceinline__ void store_process_static(ProcSmem &M, int p, const P
 {
     M.a[p] = r.a.idx;
     M.b[p] = r.b.idx;
+    M.be[p] = r.be;
     if (COMPACT) { M.ap[p] = r.a.pack; M.bp[p] = r.b.pack; }
     M.t02[p] = r.t02;
     M.shift[p] = r.shift;
@@ -189,17 +203,21 @@ __device__ __forceinline__ void store_process_static(ProcSmem &M, int p, const P
 }
 
 // Full re-gather of one process by one thread, carriers in order (the checker's summation
-// order, so refresh_interval = 1 reproduces its rates bit for bit up to pow/log); loads are
+// order, so refresh_interval = 1 reproduces its rates up to exp/log rounding); loads are
 // issued in batches of GB pairs to keep 2*GB gathers in flight per thread.
 template <bool COMPACT>
 __device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ, const unsigned *s_occp,
-                                               int C, int p, const double *fld, int field_active,
-                                               ProcSmem &M)
+                                               const int *s_occe, int C, int p, const double *fld,
+                                               int field_active, ProcSmem &M)
 {
-    constexpr int GB = 8;
-    const ProcStatic ps = load_process_static<COMPACT>(S, p % S.nn, s_occ[p / S.nn], fld, field_active);
+    constexpr int GB = 4;
+    const int c = p / S.nn;
+    Site a;
+    a.idx = s_occ[c];
+    a.pack = COMPACT ? s_occp[c] : 0u;
+    const ProcStatic ps = load_process_static<COMPACT>(S, p - c * S.nn, a, s_occe[c], fld, field_active);
     store_process_static<COMPACT>(M, p, ps);
-    const Site a = ps.a, b = ps.b;
+    const Site b = ps.b;
     double t01 = ps.vl;
     for (int c0 = 0; c0 < C; c0 += GB) {
         double pb[GB], pa[GB];
@@ -219,8 +237,15 @@ __device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ
     M.t01[p] = t01;
 }
 
+// control block written by thread 0 each step (double-buffered by step parity)
+struct StepCtl {
+    long long r0, r1;  // rows [r0, r1) of the time grid to fill with the post-hop displacement
+    int fin;           // trajectory finished
+    int pad;
+};
+
 template <int BS, bool COMPACT>
-__global__ void __launch_bounds__(BS)
+__global__ void __launch_bounds__(BS, (BS >= 128) ? 1024 / BS : 1)
 kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
 {
     const int traj = blockIdx.x;
@@ -245,17 +270,19 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     double *s_drift = sd; sd += 3 * C;
     double *s_terms = sd; sd += nn * C;   // moved carrier: per (slot, carrier) contributions
     double *s_wsum = sd; sd += 32;
-    double *s_u = sd; sd += 2;            // this step's draws
-    long long *s_ll = reinterpret_cast<long long *>(sd); sd += 2;  // rows [s_ll[0], s_ll[1]) pending
+    double *s_u = sd; sd += 4;            // [parity][u1, -log(u2)]
+    StepCtl *s_ctl = reinterpret_cast<StepCtl *>(sd); sd += 2 * (sizeof(StepCtl) / sizeof(double));
     int *si = reinterpret_cast<int *>(sd);
     M.a = si; si += n_proc;
     M.b = si; si += n_proc;
+    M.be = si; si += n_proc;
     M.ap = reinterpret_cast<unsigned *>(si); si += n_proc;
     M.bp = reinterpret_cast<unsigned *>(si); si += n_proc;
     int *s_occ = si; si += C;
+    int *s_occe = si; si += C;
     unsigned *s_occp = reinterpret_cast<unsigned *>(si); si += C;
     int *s_wfirst = si; si += 32;   // per-warp first index with cum > u1
-    int *s_flag = si; si += 2;      // [0] = selected process (tie fallback), [1] = finished
+    int *s_sel = si; si += 2;       // tie fallback result
 
     if (E.done[traj]) {
         if (tid == 0 && A.steps_done) A.steps_done[traj] = 0;
@@ -271,10 +298,34 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         fld[2] = E.field_traj[3 * traj + 2];
         field_active = (fld[0] != 0.0 || fld[1] != 0.0 || fld[2] != 0.0);
     }
+    const double two_qc = __dmul_rn(2.0, S.qc);
+    const long long steps_total = E.n_steps[traj];
+    const unsigned long long traj_gid = E.traj_id0 + (unsigned long long)traj;
+    const int R = E.refresh_interval;
+    // the thread that prepares the next step's draws while the others wait on gathers
+    const int rng_tid = (BS > 32) ? 32 : 0;
+
+    auto draw = [&](long long step_local, double *dst) {  // u1 and -log(u2) of a step
+        double u1, u2;
+        if (E.rng_mode == PYCD_RNG_REPLAY) {
+            if (step_local < A.max_steps) {
+                const double *dr = A.draws + ((long long)traj * A.max_steps + step_local) * 2;
+                u1 = dr[0];
+                u2 = dr[1];
+            } else {
+                u1 = 0.0; u2 = 1.0;
+            }
+        } else {
+            philox_uniforms(E.seed, traj_gid, (unsigned long long)(steps_total + step_local), u1, u2);
+        }
+        dst[0] = u1;
+        dst[1] = -log(u2);
+    };
 
     for (int c = tid; c < C; c += BS) {
         const int s = E.occ[(long long)traj * C + c];
         s_occ[c] = s;
+        s_occe[c] = S.site_centre[s];
         s_occp[c] = COMPACT ? S.site_pack[s] : 0u;
     }
     for (int d = tid; d < 3 * C; d += BS) {
@@ -285,65 +336,52 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     // thread-0 scalars
     double t = E.t[traj];
     long long start = E.start_idx[traj];
-    const long long steps_total = E.n_steps[traj];
     long long n_tie = 0, n_clamp = 0;
     long long step_local = 0;
-    const unsigned long long traj_gid = E.traj_id0 + (unsigned long long)traj;
-    const int R = E.refresh_interval;
-    if (tid == 0) { s_flag[1] = 0; s_ll[0] = 0; s_ll[1] = 0; }
+    int finished = 0;
+    if (tid == 0) {
+        s_ctl[0].r0 = s_ctl[0].r1 = 0; s_ctl[0].fin = 0;
+        s_ctl[1].r0 = s_ctl[1].r1 = 0; s_ctl[1].fin = 0;
+    }
+    if (tid == rng_tid) draw(0, s_u);
     __syncthreads();
 
     while (true) {
-        // ---- pending recording of the previous step (rows [rec_start, rec_end)) ----
+        const int par = (int)(step_local & 1);
+        // ---- recording decided by the previous step: rows [r0, r1) ----
         {
-            const long long r0 = s_ll[0], r1 = s_ll[1];
-            if (r1 > r0) {
+            const StepCtl ctl = s_ctl[par ^ 1];
+            if (ctl.r1 > ctl.r0) {
                 // unwrapped[start:end] = unwrapped[start-1] + displacement, core.py:2852-2854
                 for (int d = tid; d < 3 * C; d += BS) {
                     const double v = s_row[d] + s_disp[d];
                     s_row[d] = v;
                     s_disp[d] = 0.0;
                     if (E.unwrapped) {
-                        double *dst = E.unwrapped + ((long long)traj * E.n_path + r0) * 3 * C + d;
-                        for (long long r = r0; r < r1; ++r, dst += 3 * C) *dst = v;
+                        double *dst = E.unwrapped + ((long long)traj * E.n_path + ctl.r0) * 3 * C + d;
+                        for (long long r = ctl.r0; r < ctl.r1; ++r, dst += 3 * C) *dst = v;
                     }
                 }
             }
+            finished = ctl.fin;
         }
-        if (s_flag[1] || step_local >= A.max_steps) break;
-        __syncthreads();  // (1) everyone has read s_ll / s_flag before thread 0 rewrites them
+        if (finished || step_local >= A.max_steps) break;
 
-        // ---- this step's uniform draws (thread 0; broadcast through shared memory) ----
-        if (tid == 0) {
-            double u1, u2;
-            if (E.rng_mode == PYCD_RNG_REPLAY) {
-                const double *dr = A.draws + ((long long)traj * A.max_steps + step_local) * 2;
-                u1 = dr[0];
-                u2 = dr[1];
-            } else {
-                philox_uniforms(E.seed, traj_gid, (unsigned long long)(steps_total + step_local), u1, u2);
-            }
-            s_u[0] = u1;
-            s_u[1] = u2;
-        }
-
-        // ---- rates ----
+        // ---- rates + inclusive scan of the raw rates (BS-wide groups) ----
         const bool full = (R <= 1) || ((steps_total + step_local) % R == 0);
-        double carry = 0.0;   // running prefix of raw rates over BS-sized groups
-        double ktot = 0.0;
-        // pass 1: rates + inclusive scan of the raw rates (one BS-wide group at a time)
+        double carry = 0.0;
         for (int base = 0; base < n_proc; base += BS) {
             const int p = base + tid;
             double kp = 0.0;
             if (p < n_proc) {
-                if (full) gather_process<COMPACT>(S, s_occ, s_occp, C, p, fld, field_active, M);
-                const double ew = __dmul_rn(__dmul_rn(2.0, S.qc), __dadd_rn(M.t01[p], M.t02[p]));  // core.py:2016
+                if (full) gather_process<COMPACT>(S, s_occ, s_occp, s_occe, C, p, fld, field_active, M);
+                const double ew = __dmul_rn(two_qc, __dadd_rn(M.t01[p], M.t02[p]));     // core.py:2016
                 const double g0 = __dadd_rn(ew, M.shift[p]);
                 const double lam = M.lam[p];
                 const double lg = __dadd_rn(lam, g0);
                 const double gs = __dsub_rn(__dsub_rn(__ddiv_rn(__dmul_rn(lg, lg), __dmul_rn(4.0, lam)),
-                                                      M.vab[p]), M.fs[p]);                          // core.py:2045
-                kp = __dmul_rn(S.vn, pow(2.718281828459045, __ddiv_rn(-gs, kT)));                    // core.py:2047
+                                                      M.vab[p]), M.fs[p]);               // core.py:2045
+                kp = __dmul_rn(S.vn, pow_np_e(__ddiv_rn(-gs, kT)));                       // core.py:2047
                 M.k[p] = kp;
             }
             double x = kp;
@@ -353,7 +391,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                 if (lane >= o) x += y;
             }
             if (lane == 31) s_wsum[wid] = x;
-            __syncthreads();  // (2)
+            __syncthreads();  // (A)
             double pre = carry, tot = carry;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
@@ -365,8 +403,8 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             carry = tot;
             if (base + BS < n_proc) __syncthreads();  // s_wsum reused by the next group
         }
-        ktot = carry;
-        const double u1 = s_u[0], u2 = s_u[1];
+        const double ktot = carry;
+        const double u1 = s_u[2 * par], nlog_u2 = s_u[2 * par + 1];
 
         // ---- first index with cumsum(k/k_total) > u1, core.py:2797-2800 ----
         int first = INT_MAX;
@@ -377,7 +415,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             if (m && first == INT_MAX) first = base + wid * 32 + (__ffs(m) - 1);
         }
         if (lane == 0) s_wfirst[wid] = first;
-        __syncthreads();  // (3) M.cum, s_wfirst visible
+        __syncthreads();  // (B) M.cum, s_wfirst visible
         int sel = INT_MAX;
 #pragma unroll
         for (int w = 0; w < NW; ++w) sel = min(sel, s_wfirst[w]);
@@ -398,10 +436,10 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                 }
                 if (s2 < 0) { s2 = n_proc - 1; ++n_clamp; }  // the reference raises IndexError here
                 ++n_tie;
-                s_flag[0] = s2;
+                s_sel[0] = s2;
             }
             __syncthreads();
-            sel = s_flag[0];
+            sel = s_sel[0];
         }
 
         const int cs = sel / nn, slot = sel - cs * nn;
@@ -410,13 +448,22 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         b_new.idx = M.b[sel];
         a_old.pack = COMPACT ? M.ap[sel] : 0u;
         b_new.pack = COMPACT ? M.bp[sel] : 0u;
+        const int e_new = M.be[sel];
         const bool next_full = (R <= 1) || ((steps_total + step_local + 1) % R == 0);
 
-        // ---- issue the long-latency gathers of the incremental update first ----
-        // (a) untouched processes: 4 elements each
+        // ---- issue the long-latency loads of this step's tail first ----
+        double hv0 = 0.0, hv1 = 0.0, hv2 = 0.0;
+        if (tid == 0) {  // hop vector of the selected process (consumed after barrier C)
+            const double *hv = S.hopvec + ((long long)s_occe[cs] * nn + slot) * 3;
+            hv0 = __ldg(hv); hv1 = __ldg(hv + 1); hv2 = __ldg(hv + 2);
+        }
         double patch[4];
         int npatch = 0;
+        ProcStatic moved;
+        const int my_slot = wid + lane * NW;   // lane j of warp w <-> slot w + j*NW of the moved carrier
+        const bool has_slot = !next_full && my_slot < nn;
         if (!next_full) {
+            // (a) untouched processes: 4 elements each
             for (int p = tid; p < n_proc && npatch < 4; p += BS) {
                 double v = 0.0;
                 if (p / nn != cs) {
@@ -431,55 +478,52 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                 patch[npatch++] = v;
             }
             // (b) the moved carrier's nn processes: (slot, carrier) items over the whole block
-            const int e_new = __ldg(S.site_centre + b_new.idx);
             for (int item = tid; item < nn * C; item += BS) {
                 const int sl = item / C, c2 = item - sl * C;
-                const Site nbr = make_site<COMPACT>(S, __ldg(S.neigh + (long long)e_new * nn + sl));
+                Site nbr;
+                nbr.idx = __ldg(S.neigh + (long long)e_new * nn + sl);
+                nbr.pack = COMPACT ? __ldg(S.neigh_pack + (long long)e_new * nn + sl) : 0u;
                 Site sc;
                 if (c2 == cs) sc = b_new;
                 else { sc.idx = s_occ[c2]; sc.pack = COMPACT ? s_occp[c2] : 0u; }
                 s_terms[item] = S.qc * (ld_pair<COMPACT>(S, nbr, sc) - ld_pair<COMPACT>(S, b_new, sc));
             }
+            // (c) static parts of the moved carrier's new processes
+            if (has_slot) moved = load_process_static<COMPACT>(S, my_slot, b_new, e_new, fld, field_active);
         }
 
-        // (c) static parts of the moved carrier's new processes: lane j of warp w <-> slot w + j*NW
-        ProcStatic moved;
-        const int my_slot = wid + lane * NW;
-        const bool has_slot = !next_full && my_slot < nn;
-        if (has_slot) moved = load_process_static<COMPACT>(S, my_slot, b_new.idx, fld, field_active);
-
-        // ---- thread 0: time advance + bookkeeping, core.py:2802-2830, 2844-2861 ----
+        // ---- thread 0: time advance, grid bookkeeping, core.py:2802-2804, 2848-2861 ----
         if (tid == 0) {
-            t -= log(u2) / ktot;
+            t += nlog_u2 / ktot;
             const long long end = (long long)(t / E.dt_grid);
-            const int e = S.site_centre[a_old.idx];
-            const double *hv = S.hopvec + ((long long)e * nn + slot) * 3;
+            StepCtl ctl;
+            ctl.r0 = 0; ctl.r1 = 0; ctl.fin = 0; ctl.pad = 0;
+            if (end >= start + 1) {
+                const long long e2 = end >= E.n_path ? E.n_path : end;
+                if (start < E.n_path) { ctl.r0 = start; ctl.r1 = e2; }
+                start = e2;
+            }
+            if (E.stop_at_grid_end && end >= E.n_path) ctl.fin = 1;
+            if (E.step_limit > 0 && steps_total + step_local + 1 >= E.step_limit) ctl.fin = 1;
+            s_ctl[par] = ctl;
+        }
+        // ---- next step's draws (off the critical path: the block is waiting on gathers) ----
+        if (tid == rng_tid) draw(step_local + 1, s_u + 2 * (par ^ 1));
+        __syncthreads();  // (C) s_terms, s_ctl visible; everyone is done with s_occ[cs] / M.*[sel]
+
+        // ---- bring the cached sums up to date for the next step ----
+        if (tid == 0) {  // core.py:2810-2830, 2844-2845
             const double kp = M.k[sel];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                s_disp[3 * cs + d] += hv[d];
-                if (field_active) s_drift[3 * cs + d] += hv[d] * kp;
+            s_disp[3 * cs] += hv0; s_disp[3 * cs + 1] += hv1; s_disp[3 * cs + 2] += hv2;
+            if (field_active) {
+                s_drift[3 * cs] += hv0 * kp; s_drift[3 * cs + 1] += hv1 * kp; s_drift[3 * cs + 2] += hv2 * kp;
             }
             if (A.events_out) A.events_out[(long long)traj * A.max_steps + step_local] = sel;
             if (A.times_out) A.times_out[(long long)traj * A.max_steps + step_local] = t;
-            long long r0 = 0, r1 = 0;
-            int fin = 0;
-            if (end >= start + 1) {  // core.py:2848-2861
-                const long long e2 = end >= E.n_path ? E.n_path : end;
-                if (start < E.n_path) { r0 = start; r1 = e2; }
-                start = e2;
-            }
-            if (E.stop_at_grid_end && end >= E.n_path) fin = 1;
-            if (E.step_limit > 0 && steps_total + step_local + 1 >= E.step_limit) fin = 1;
-            s_ll[0] = r0;
-            s_ll[1] = r1;
-            s_flag[1] = fin;
             s_occ[cs] = b_new.idx;
+            s_occe[cs] = e_new;
             if (COMPACT) s_occp[cs] = b_new.pack;
         }
-        __syncthreads();  // (4) s_terms, s_occ, s_ll, s_flag visible
-
-        // ---- bring the cached sums up to date for the next step ----
         if (!next_full) {
             int ip = 0;
             for (int p = tid; p < n_proc; p += BS, ++ip) {
@@ -510,7 +554,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             }
         }
         ++step_local;
-        __syncthreads();  // (5)
+        __syncthreads();  // (D)
     }
 
     // ---- write the state back ----
@@ -529,7 +573,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         E.n_steps[traj] = steps_total + step_local;
         E.near_tie[traj] += n_tie;
         E.clamped[traj] += n_clamp;
-        if (s_flag[1]) E.done[traj] = 1;
+        if (finished) E.done[traj] = 1;
         if (A.steps_done) A.steps_done[traj] = step_local;
     }
 }
@@ -565,8 +609,8 @@ vlat_kernel(const double *__restrict__ P, const double *__restrict__ q, long lon
 }
 
 static size_t kmc_smem_bytes(int n_proc, int C, int nn) {
-    const size_t doubles = (size_t)8 * n_proc + (size_t)9 * C + (size_t)nn * C + 32 + 2 + 2;
-    const size_t ints = (size_t)4 * n_proc + 2 * (size_t)C + 32 + 2;
+    const size_t doubles = (size_t)8 * n_proc + (size_t)9 * C + (size_t)nn * C + 32 + 4 + 2 * 3;
+    const size_t ints = (size_t)5 * n_proc + 3 * (size_t)C + 32 + 2;
     return doubles * 8 + ((ints + 1) / 2) * 8;
 }
 
@@ -578,6 +622,12 @@ __global__ void site_pack_kernel(unsigned *out, long long n, int nb, int sy, int
     const int cell = (int)(i / nb), b = (int)(i - (long long)cell * nb);
     const int z = cell % sz, y = (cell / sz) % sy, x = cell / (sz * sy);
     out[i] = (unsigned)b | ((unsigned)x << 8) | ((unsigned)y << 16) | ((unsigned)z << 24);
+}
+
+__global__ void neigh_pack_kernel(const int *neigh, const unsigned *site_pack, long long n, unsigned *out)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = site_pack[neigh[i]];
 }
 
 }  // namespace pycd
@@ -593,7 +643,7 @@ struct pycd_kmc_system {
     InBuf<int> site_centre, site_class, neigh;
     InBuf<double> hopvec, lam, vab, e_rel;
     DevBuf<double> v_lat;
-    DevBuf<unsigned> site_pack;
+    DevBuf<unsigned> site_pack, neigh_pack;
     bool compact = false;
 };
 
@@ -645,6 +695,13 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             sys->lam.bind(d->lam, (size_t)d->n_class * d->nn, s);
             sys->vab.bind(d->vab, (size_t)d->n_class * d->nn, s);
             sys->e_rel.bind(d->e_rel, n, s);
+            if (sys->compact) {
+                const long long nn_tot = (long long)d->n_centres * d->nn;
+                sys->neigh_pack.alloc((size_t)nn_tot);
+                neigh_pack_kernel<<<(unsigned)((nn_tot + 255) / 256), 256, 0, s>>>(sys->neigh.p, sys->site_pack.p,
+                                                                                  nn_tot, sys->neigh_pack.p);
+                check_launch(ctx, "neigh_pack_kernel");
+            }
             InBuf<double> q;
             q.bind(d->q_lat, n, s);
             // V_lat = P . q_lat: one entry per site (dense) or per basis site (compact: the
@@ -666,6 +723,7 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             for (int k = 0; k < 3; ++k) v.field[k] = d->field[k];
             v.field_active = d->field_active;
             v.site_pack = sys->site_pack.p;
+            v.neigh_pack = sys->neigh_pack.p;
             v.n_basis = d->n_basis; v.sx = d->size[0]; v.sy = d->size[1]; v.sz = d->size[2];
             sys->n_centres = d->n_centres;
             sys->n_class = d->n_class;
