@@ -32,8 +32,7 @@ struct EwaldTile {
     static_assert(TX * TY == EW_THREADS, "tile/thread shape mismatch");
     static_assert(TM % 2 == 0 && TN % 2 == 0, "double2 operand loads");
     static constexpr size_t smem_bytes =
-        sizeof(double) * (size_t)(2 * KC) * (BM + BN) + sizeof(KEntry) * KC + sizeof(double) * KC +
-        sizeof(double) * 2 * (BM + BN);
+        sizeof(double) * (size_t)(2 * KC) * (BM + BN) + sizeof(KEntry) * KC + sizeof(double) * KC;
 };
 
 // theta[j][a] = B_a . r_j  so that k_n . r_j = n1*theta_j0 + n2*theta_j1 + n3*theta_j2
@@ -50,11 +49,37 @@ __global__ void ewald_theta_kernel(const double *__restrict__ coords, long long 
     theta[3 * j + 2] = b20 * x + b21 * y + b22 * z;
 }
 
+// (cos, sin)(k.r) of one site along a run of the k list: a sincos where a run starts, one
+// complex multiply by e^{i theta_3} where the entry continues the previous one along n3.
+struct PhaseWalker {
+    double t1, t2, t3, c3, s3, c, s;
+    __device__ __forceinline__ void init(const double *__restrict__ theta, long long site) {
+        t1 = theta[3 * site]; t2 = theta[3 * site + 1]; t3 = theta[3 * site + 2];
+        sincos(t3, &s3, &c3);
+        c = 1.0; s = 0.0;
+    }
+    __device__ __forceinline__ void step(const KEntry ke, bool restart) {
+        if (restart || !(ke.flag & 1)) {
+            const double arg = fma((double)ke.n1, t1, fma((double)ke.n2, t2, (double)ke.n3 * t3));
+            sincos(arg, &s, &c);
+        } else {
+            const double cn = c * c3 - s * s3;
+            s = fma(s, c3, c * s3);
+            c = cn;
+        }
+    }
+};
+
 // Reciprocal-space partial sums.  grid = k_split * n_row_tiles * n_col_tiles CTAs of
 // 256 threads; CTA (ks, rt, ct) accumulates its share of the k chunks for the
 // BM x BN tile and writes out[ks][row][col] (un-scaled: sum_k w_k cos(k.d_ij)).
-template <int BM, int BN, int TM, int TN, int KC, int SUB>
-__global__ void __launch_bounds__(EW_THREADS, 1)
+// Panel generation: thread t walks tile site t (rows first, then columns) through every
+// entry of the chunk, carrying its phase across chunks; when the tile has more sites than
+// threads (skinny tile: BN = 256 columns + BM rows) the BM row sites are walked in
+// KC/ (256/BM)-entry pieces by all threads.  CTAS CTAs share an SM so that one CTA's panel
+// generation overlaps another's DFMA phase.
+template <int BM, int BN, int TM, int TN, int KC, int CTAS>
+__global__ void __launch_bounds__(EW_THREADS, CTAS)
 ewald_fourier_kernel(const double *__restrict__ theta, long long n_sites, long long row0,
                      long long n_rows, const KEntry *__restrict__ kent,
                      const double *__restrict__ kw, int n_chunks, int k_split, int n_row_tiles,
@@ -62,14 +87,17 @@ ewald_fourier_kernel(const double *__restrict__ theta, long long n_sites, long l
 {
     using T = EwaldTile<BM, BN, TM, TN, KC>;
     constexpr int TX = T::TX, TY = T::TY;
-    constexpr int NS = BM + BN;
-    static_assert(KC % SUB == 0, "sub-chunk must divide chunk");
+    constexpr bool SPLIT_ROWS = (BM + BN > EW_THREADS);   // skinny tile
+    static_assert(!SPLIT_ROWS || BN == EW_THREADS, "skinny tile: one column site per thread");
+    static_assert(SPLIT_ROWS || BM + BN == EW_THREADS, "dense tile: one tile site per thread");
+    constexpr int ROW_PIECES = SPLIT_ROWS ? EW_THREADS / BM : 1;
+    constexpr int PIECE = KC / ROW_PIECES;
+    static_assert(!SPLIT_ROWS || (KC % ROW_PIECES == 0 && PIECE >= 1), "row pieces must tile the chunk");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *As = reinterpret_cast<double *>(smem_raw);  // [2*KC][BM]  rows, weighted
     double *Bs = As + 2 * KC * BM;                       // [2*KC][BN]  columns
     double *s_w = Bs + 2 * KC * BN;                      // [KC]
-    double *s_z3 = s_w + KC;                             // [NS][2]  e^{i theta_3} per tile site
-    KEntry *s_ent = reinterpret_cast<KEntry *>(s_z3 + 2 * NS);  // [KC]
+    KEntry *s_ent = reinterpret_cast<KEntry *>(s_w + KC);  // [KC]
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
@@ -81,16 +109,21 @@ ewald_fourier_kernel(const double *__restrict__ theta, long long n_sites, long l
     const int c1 = (int)(((long long)(ks + 1) * n_chunks) / k_split);
 
     // tile-site -> global site (clamped; out-of-range results are never stored)
-    auto tile_site = [&](int sl) -> long long {
-        long long s = (sl < BM) ? (row0 + (long long)rt * BM + sl) : ((long long)ct * BN + (sl - BM));
+    auto row_site = [&](int r) -> long long {
+        const long long s = row0 + (long long)rt * BM + r;
         return s < n_sites ? s : n_sites - 1;
     };
-    for (int sl = tid; sl < NS; sl += EW_THREADS) {
-        double s3, c3;
-        sincos(theta[3 * tile_site(sl) + 2], &s3, &c3);
-        s_z3[2 * sl] = c3;
-        s_z3[2 * sl + 1] = s3;
-    }
+    auto col_site = [&](int c) -> long long {
+        const long long s = (long long)ct * BN + c;
+        return s < n_sites ? s : n_sites - 1;
+    };
+    // primary walker: dense tile -> tile site tid (rows then columns); skinny -> column tid
+    const bool prim_is_row = !SPLIT_ROWS && tid < BM;
+    const int prim_idx = SPLIT_ROWS ? tid : (prim_is_row ? tid : tid - BM);
+    PhaseWalker pw, rw;
+    pw.init(theta, prim_is_row ? row_site(prim_idx) : col_site(prim_idx));
+    const int r_site = tid % BM, r_piece = tid / BM;      // skinny: row walker assignment
+    if (SPLIT_ROWS) rw.init(theta, row_site(r_site));
 
     double acc[TM][TN];
 #pragma unroll
@@ -105,55 +138,55 @@ ewald_fourier_kernel(const double *__restrict__ theta, long long n_sites, long l
             s_w[tid] = kw[(long long)chunk * KC + tid];
         }
         __syncthreads();
-        // ---- generate panels: item = (tile site, sub-chunk of SUB consecutive k) ----
-        for (int item = tid; item < NS * (KC / SUB); item += EW_THREADS) {
-            const int sl = item % NS, sub = item / NS;
-            const long long site = tile_site(sl);
-            const double t1 = theta[3 * site], t2 = theta[3 * site + 1], t3 = theta[3 * site + 2];
-            const double c3 = s_z3[2 * sl], s3 = s_z3[2 * sl + 1];
-            double c = 1.0, s = 0.0;
+        // ---- generate the operand panels ----
 #pragma unroll 4
-            for (int e = sub * SUB; e < (sub + 1) * SUB; ++e) {
-                const KEntry ke = s_ent[e];
-                if (e == sub * SUB || !(ke.flag & 1)) {
-                    const double arg = fma((double)ke.n1, t1, fma((double)ke.n2, t2, (double)ke.n3 * t3));
-                    sincos(arg, &s, &c);
-                } else {
-                    const double cn = c * c3 - s * s3;
-                    s = s * c3 + c * s3;
-                    c = cn;
-                }
-                if (sl < BM) {
-                    const double w = s_w[e];
-                    As[e * BM + sl] = w * c;
-                    As[(KC + e) * BM + sl] = w * s;
-                } else {
-                    Bs[e * BN + (sl - BM)] = c;
-                    Bs[(KC + e) * BN + (sl - BM)] = s;
-                }
+        for (int e = 0; e < KC; ++e) {
+            pw.step(s_ent[e], chunk == c0 && e == 0);
+            if (prim_is_row) {
+                const double w = s_w[e];
+                As[e * BM + prim_idx] = w * pw.c;
+                As[(KC + e) * BM + prim_idx] = w * pw.s;
+            } else {
+                Bs[e * BN + prim_idx] = pw.c;
+                Bs[(KC + e) * BN + prim_idx] = pw.s;
+            }
+        }
+        if (SPLIT_ROWS) {
+#pragma unroll
+            for (int q = 0; q < PIECE; ++q) {
+                const int e = r_piece * PIECE + q;
+                rw.step(s_ent[e], q == 0);
+                const double w = s_w[e];
+                As[e * BM + r_site] = w * rw.c;
+                As[(KC + e) * BM + r_site] = w * rw.s;
             }
         }
         __syncthreads();
-        // ---- rank-2KC update of the register tile ----
-#pragma unroll 4
-        for (int kk = 0; kk < 2 * KC; ++kk) {
-            double a[TM], b[TN];
+        // ---- rank-2KC update of the register tile, operands double-buffered in registers ----
+        double a[2][TM], b[2][TN];
+        auto load_ab = [&](int buf, int kk) {
 #pragma unroll
             for (int i = 0; i < TM / 2; ++i) {
                 const double2 v = *reinterpret_cast<const double2 *>(&As[kk * BM + i * 2 * TY + 2 * ty]);
-                a[2 * i] = v.x;
-                a[2 * i + 1] = v.y;
+                a[buf][2 * i] = v.x;
+                a[buf][2 * i + 1] = v.y;
             }
 #pragma unroll
             for (int j = 0; j < TN / 2; ++j) {
                 const double2 v = *reinterpret_cast<const double2 *>(&Bs[kk * BN + j * 2 * TX + 2 * tx]);
-                b[2 * j] = v.x;
-                b[2 * j + 1] = v.y;
+                b[buf][2 * j] = v.x;
+                b[buf][2 * j + 1] = v.y;
             }
+        };
+        load_ab(0, 0);
+        constexpr int UNR = (TM * TN >= 64) ? 8 : 2 * KC;   // keep the loop body inside the i-cache
+#pragma unroll(UNR)
+        for (int kk = 0; kk < 2 * KC; ++kk) {
+            if (kk + 1 < 2 * KC) load_ab((kk + 1) & 1, kk + 1);
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[kk & 1][i], b[kk & 1][j], acc[i][j]);
         }
     }
 
@@ -257,7 +290,7 @@ static void invert3(const double *m, double *inv) {
 // (cos is even); the reference keeps the lexicographically negative triples
 // (core.py:816-838), here the half space is n3>0 | (n3==0,n2>0) | (n3==n2==0,n1>0)
 // so that runs along n3 are contiguous.
-static int64_t build_k_list(const pycd_ewald_desc &d, int kc, int sub, std::vector<KEntry> &ent,
+static int64_t build_k_list(const pycd_ewald_desc &d, int kc, std::vector<KEntry> &ent,
                             std::vector<double> &w) {
     const double alpha4 = 4 * d.alpha;
     const double coeff = (2 * M_PI) / d.volume;
@@ -277,7 +310,7 @@ static int64_t build_k_list(const pycd_ewald_desc &d, int kc, int sub, std::vect
                 if (!(k2 < kc2)) continue;
                 KEntry e;
                 e.n1 = (short)n1; e.n2 = (short)n2; e.n3 = (short)n3;
-                const bool cont = (prev == n3 - 1) && (ent.size() % (size_t)sub != 0);
+                const bool cont = (prev == n3 - 1);
                 e.flag = cont ? 1 : 0;
                 ent.push_back(e);
                 w.push_back(coeff * exp(-k2 / alpha4) / k2);  // core.py:869-875
@@ -293,12 +326,12 @@ static int64_t build_k_list(const pycd_ewald_desc &d, int kc, int sub, std::vect
     return k_eff;
 }
 
-template <int BM, int BN, int TM, int TN, int KC, int SUB>
+template <int BM, int BN, int TM, int TN, int KC, int CTAS>
 static void launch_fourier(pycd_ctx *ctx, const double *theta, long long n, long long row0,
                            long long n_rows, const KEntry *kent, const double *kw, int n_chunks,
                            int k_split, double *out) {
     using T = EwaldTile<BM, BN, TM, TN, KC>;
-    auto kern = ewald_fourier_kernel<BM, BN, TM, TN, KC, SUB>;
+    auto kern = ewald_fourier_kernel<BM, BN, TM, TN, KC, CTAS>;
     PYCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::smem_bytes));
     const int n_row_tiles = (int)((n_rows + BM - 1) / BM), n_col_tiles = (int)((n + BN - 1) / BN);
     const long long grid = (long long)k_split * n_row_tiles * n_col_tiles;
@@ -321,14 +354,14 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         PYCD_REQUIRE(desc->alpha > 0 && desc->volume > 0 && desc->dielectric > 0, "bad Ewald parameters");
         DeviceGuard g(ctx);
         const long long n_rows = row_end - row_begin;
-        constexpr int KC = 32;
-        // wide tile for big row blocks, skinny tile (rows of one unit cell) otherwise
+        // wide tile (128x128, 32-entry chunks, 1 CTA/SM) for big row blocks, skinny tile
+        // (32x256, 16-entry chunks, 2 CTAs/SM) for the rows of one unit cell
         const bool wide = n_rows > 64;
-        const int sub = wide ? 32 : 8;
+        const int KC = wide ? 32 : 16;
 
         std::vector<KEntry> ent;
         std::vector<double> w;
-        const int64_t k_eff = build_k_list(*desc, KC, sub, ent, w);
+        const int64_t k_eff = build_k_list(*desc, KC, ent, w);
         const int n_chunks = (int)(ent.size() / KC);
 
         InBuf<double> coords;
@@ -357,12 +390,12 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
             // candidates pick the best-filled last wave, preferring fewer splits on ties
             const long long ws_cap = std::max(1ll, (1ll << 30) / (n_rows * n * 8));
             const long long ks_max = std::min({(long long)n_chunks, ws_cap, 32ll});
+            const long long slots = (long long)ctx->n_sm * (wide ? 1 : 2);
             double best_fill = -1.0;
             for (long long ks = 1; ks <= ks_max; ++ks) {
                 const long long grid = tiles * ks;
-                const long long waves = (grid + ctx->n_sm - 1) / ctx->n_sm;
-                double fill = (double)grid / (double)(waves * ctx->n_sm);
-                if (grid < ctx->n_sm) fill = (double)grid / ctx->n_sm;
+                const long long waves = (grid + slots - 1) / slots;
+                const double fill = (double)grid / (double)(waves * slots);
                 if (fill > best_fill + 0.02) { best_fill = fill; k_split = (int)ks; }
             }
         }
@@ -375,10 +408,10 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         KernelTimer tf(ctx, KC_EWALD_FOURIER);
         if (n_chunks > 0) {
             if (wide)
-                launch_fourier<128, 128, 8, 8, KC, 32>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
-                                                      n_chunks, k_split, partials);
+                launch_fourier<128, 128, 8, 8, 32, 1>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                     n_chunks, k_split, partials);
             else
-                launch_fourier<32, 256, 8, 4, KC, 8>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                launch_fourier<32, 256, 8, 4, 16, 2>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
                                                     n_chunks, k_split, partials);
         } else {
             PYCD_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * n_rows * n, ctx->stream));

@@ -164,11 +164,11 @@ struct ProcStatic {
 
 // a = current site of the carrier (index, pack, centre index e known to the caller)
 template <bool COMPACT>
-__device__ __forceinline__ ProcStatic load_process_static(const SysDev &S, int slot, Site a, int e,
+__device__ __forceinline__ ProcStatic load_process_static(const SysDev &S, int nn, int slot, Site a, int e,
                                                           const double *fld, int field_active)
 {
     ProcStatic r;
-    const long long ns = (long long)e * S.nn + slot;
+    const long long ns = (long long)e * nn + slot;
     r.a = a;
     r.b.idx = __ldg(S.neigh + ns);
     r.b.pack = COMPACT ? __ldg(S.neigh_pack + ns) : 0u;
@@ -176,8 +176,8 @@ __device__ __forceinline__ ProcStatic load_process_static(const SysDev &S, int s
     r.be = __ldg(S.site_centre + r.b.idx);
     r.t02 = __dmul_rn(S.qc, __dsub_rn(ld_pair<COMPACT>(S, a, a), ld_pair<COMPACT>(S, a, r.b)));
     r.shift = __dsub_rn(__ldg(S.e_rel + r.b.idx), __ldg(S.e_rel + a.idx));
-    r.lam = __ldg(S.lam + cls * S.nn + slot);
-    r.vab = __ldg(S.vab + cls * S.nn + slot);
+    r.lam = __ldg(S.lam + cls * nn + slot);
+    r.vab = __ldg(S.vab + cls * nn + slot);
     r.fs = 0.0;
     if (field_active) {
         const double *hv = S.hopvec + ns * 3;
@@ -207,15 +207,15 @@ __device__ __forceinline__ void store_process_static(ProcSmem &M, int p, const P
 // issued in batches of GB pairs to keep 2*GB gathers in flight per thread.
 template <bool COMPACT>
 __device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ, const unsigned *s_occp,
-                                               const int *s_occe, int C, int p, const double *fld,
+                                               const int *s_occe, int C, int nn, int p, const double *fld,
                                                int field_active, ProcSmem &M)
 {
     constexpr int GB = 4;
-    const int c = p / S.nn;
+    const int c = p / nn;
     Site a;
     a.idx = s_occ[c];
     a.pack = COMPACT ? s_occp[c] : 0u;
-    const ProcStatic ps = load_process_static<COMPACT>(S, p - c * S.nn, a, s_occe[c], fld, field_active);
+    const ProcStatic ps = load_process_static<COMPACT>(S, nn, p - c * nn, a, s_occe[c], fld, field_active);
     store_process_static<COMPACT>(M, p, ps);
     const Site b = ps.b;
     double t01 = ps.vl;
@@ -244,13 +244,17 @@ struct StepCtl {
     int pad;
 };
 
-template <int BS, bool COMPACT>
+// CT / NNT: compile-time carrier count / neighbour slots (0 = run-time values); the
+// specialisation folds the shared-memory layout and the index divisions into constants.
+template <int BS, bool COMPACT, int CT, int NNT>
 __global__ void __launch_bounds__(BS, (BS >= 128) ? 1024 / BS : 1)
 kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
 {
     const int traj = blockIdx.x;
     const int tid = threadIdx.x;
-    const int C = E.C, n_proc = E.n_proc, nn = S.nn;
+    const int C = CT ? CT : E.C;
+    const int nn = NNT ? NNT : S.nn;
+    const int n_proc = (CT && NNT) ? CT * NNT : E.n_proc;
     constexpr int NW = BS / 32;
     const int lane = tid & 31, wid = tid >> 5;
 
@@ -339,6 +343,8 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     long long n_tie = 0, n_clamp = 0;
     long long step_local = 0;
     int finished = 0;
+    // steps until the next full re-gather (launches start on a multiple of R)
+    int to_refresh = (R <= 1) ? 0 : (int)((R - (steps_total % R)) % R);
     if (tid == 0) {
         s_ctl[0].r0 = s_ctl[0].r1 = 0; s_ctl[0].fin = 0;
         s_ctl[1].r0 = s_ctl[1].r1 = 0; s_ctl[1].fin = 0;
@@ -368,13 +374,14 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         if (finished || step_local >= A.max_steps) break;
 
         // ---- rates + inclusive scan of the raw rates (BS-wide groups) ----
-        const bool full = (R <= 1) || ((steps_total + step_local) % R == 0);
+        const bool full = (to_refresh == 0);
+        to_refresh = (R <= 1) ? 0 : (full ? R - 1 : to_refresh - 1);
         double carry = 0.0;
         for (int base = 0; base < n_proc; base += BS) {
             const int p = base + tid;
             double kp = 0.0;
             if (p < n_proc) {
-                if (full) gather_process<COMPACT>(S, s_occ, s_occp, s_occe, C, p, fld, field_active, M);
+                if (full) gather_process<COMPACT>(S, s_occ, s_occp, s_occe, C, nn, p, fld, field_active, M);
                 const double ew = __dmul_rn(two_qc, __dadd_rn(M.t01[p], M.t02[p]));     // core.py:2016
                 const double g0 = __dadd_rn(ew, M.shift[p]);
                 const double lam = M.lam[p];
@@ -405,12 +412,15 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         }
         const double ktot = carry;
         const double u1 = s_u[2 * par], nlog_u2 = s_u[2 * par + 1];
+        // cum/k_total > u1  <=>  cum > u1*k_total up to rounding; draws within TIE_TOL of an
+        // edge are re-decided below in the reference's sequential order
+        const double thresh = u1 * ktot, tie_w = TIE_TOL * ktot;
 
         // ---- first index with cumsum(k/k_total) > u1, core.py:2797-2800 ----
         int first = INT_MAX;
         for (int base = 0; base < n_proc; base += BS) {
             const int p = base + tid;
-            const bool hit = (p < n_proc) && (__ddiv_rn(M.cum[p], ktot) > u1);
+            const bool hit = (p < n_proc) && (M.cum[p] > thresh);
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m && first == INT_MAX) first = base + wid * 32 + (__ffs(m) - 1);
         }
@@ -421,8 +431,8 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         for (int w = 0; w < NW; ++w) sel = min(sel, s_wfirst[w]);
         bool tie = (sel == INT_MAX);
         if (!tie) {
-            const double hi = M.cum[sel] / ktot, lo = sel > 0 ? M.cum[sel - 1] / ktot : 0.0;
-            tie = (hi - u1 < TIE_TOL) || (sel > 0 && u1 - lo < TIE_TOL);
+            const double hi = M.cum[sel], lo = sel > 0 ? M.cum[sel - 1] : 0.0;
+            tie = (hi - thresh < tie_w) || (sel > 0 && thresh - lo < tie_w);
         }
         if (tie) {  // block-uniform: redo the selection in the reference's sequential order
             if (tid == 0) {
@@ -449,7 +459,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         a_old.pack = COMPACT ? M.ap[sel] : 0u;
         b_new.pack = COMPACT ? M.bp[sel] : 0u;
         const int e_new = M.be[sel];
-        const bool next_full = (R <= 1) || ((steps_total + step_local + 1) % R == 0);
+        const bool next_full = (to_refresh == 0);
 
         // ---- issue the long-latency loads of this step's tail first ----
         double hv0 = 0.0, hv1 = 0.0, hv2 = 0.0;
@@ -489,7 +499,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                 s_terms[item] = S.qc * (ld_pair<COMPACT>(S, nbr, sc) - ld_pair<COMPACT>(S, b_new, sc));
             }
             // (c) static parts of the moved carrier's new processes
-            if (has_slot) moved = load_process_static<COMPACT>(S, my_slot, b_new, e_new, fld, field_active);
+            if (has_slot) moved = load_process_static<COMPACT>(S, nn, my_slot, b_new, e_new, fld, field_active);
         }
 
         // ---- thread 0: time advance, grid bookkeeping, core.py:2802-2804, 2848-2861 ----
@@ -852,9 +862,9 @@ extern "C" int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens) {
     });
 }
 
-template <int BS, bool COMPACT>
+template <int BS, bool COMPACT, int CT, int NNT>
 static void launch_step_impl(pycd_ctx *ctx, const SysDev &S, const EnsDev &E, const AdvanceArgs &A, size_t smem) {
-    auto kern = kmc_step_kernel<BS, COMPACT>;
+    auto kern = kmc_step_kernel<BS, COMPACT, CT, NNT>;
     if (smem > 48 * 1024)
         PYCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)E.n_traj, BS, smem, ctx->stream>>>(S, E, A);
@@ -864,8 +874,8 @@ static void launch_step_impl(pycd_ctx *ctx, const SysDev &S, const EnsDev &E, co
 template <int BS>
 static void launch_step(pycd_ctx *ctx, bool compact, const SysDev &S, const EnsDev &E, const AdvanceArgs &A,
                         size_t smem) {
-    if (compact) launch_step_impl<BS, true>(ctx, S, E, A, smem);
-    else launch_step_impl<BS, false>(ctx, S, E, A, smem);
+    if (compact) launch_step_impl<BS, true, 0, 0>(ctx, S, E, A, smem);
+    else launch_step_impl<BS, false, 0, 0>(ctx, S, E, A, smem);
 }
 
 extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
@@ -905,6 +915,8 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         if (E.n_proc <= 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (E.n_proc <= 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (E.n_proc <= 128) launch_step<128>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (E.C == 64 && ens->sys->dev.nn == 4 && cp)   // the benchmark shape: fully specialised
+            launch_step_impl<256, true, 64, 4>(ctx, ens->sys->dev, E, A, smem);
         else launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
         tk.stop(1);
         ev.finish(s);
