@@ -54,6 +54,11 @@ double pycd_ctx_total_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
 int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t kernel_class);
 int pycd_ctx_reset_timers(pycd_ctx *ctx);
 
+/* Page-locked host buffers for the end-to-end path (host numpy views over them make the
+ * H2D/D2H copies of a call run at PCIe speed instead of through pageable staging). */
+int pycd_host_alloc(int64_t bytes, void **out);
+int pycd_host_free(void *ptr);
+
 /* ---- Ewald site-pair array --------------------------------------------- */
 /* Replaces System.pot_r_ewald / pot_k_ewald / get_precomputed_array
  * (PyCD/core.py:799-878, 1594-1602, 1659-1661).  Pair vectors are never

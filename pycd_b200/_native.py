@@ -106,6 +106,8 @@ _SIGNATURES = {
     'pycd_ctx_total_kernel_ms': (C.c_double, [C.c_void_p, C.c_int32]),
     'pycd_ctx_class_launches': (C.c_int64, [C.c_void_p, C.c_int32]),
     'pycd_ctx_reset_timers': (C.c_int, [C.c_void_p]),
+    'pycd_host_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    'pycd_host_free': (C.c_int, [C.c_void_p]),
     'pycd_ewald_rows': (C.c_int, [C.c_void_p, C.POINTER(EwaldDesc), C.c_int64, C.c_int64,
                                   C.c_void_p, C.POINTER(EwaldStats)]),
     'pycd_ewald_expand': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
@@ -166,6 +168,16 @@ def ptr(a):
             raise ValueError('tensor must be contiguous')
         return a.data_ptr()
     raise TypeError(f'cannot take a pointer of {type(a)}')
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory (kept alive for the life of the process)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().pycd_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Context:

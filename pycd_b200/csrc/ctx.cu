@@ -100,6 +100,19 @@ int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t k) {
     return (ctx && k >= 0 && k < KC_COUNT) ? ctx->class_launches[k] : -1;
 }
 
+int pycd_host_alloc(int64_t bytes, void **out) {
+    return guarded([&] {
+        PYCD_REQUIRE(out && bytes > 0, "bad pinned allocation request");
+        PYCD_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    });
+}
+
+int pycd_host_free(void *ptr) {
+    return guarded([&] {
+        if (ptr) PYCD_CUDA(cudaFreeHost(ptr));
+    });
+}
+
 int pycd_ctx_reset_timers(pycd_ctx *ctx) {
     if (!ctx) return 1;
     for (int k = 0; k < KC_COUNT; ++k) {

@@ -279,13 +279,25 @@ class KmcEnsemble:
                                              C.byref(n_active)))
         return n_active.value
 
-    def read(self, unwrapped=True, rates=False):
+    def read(self, unwrapped=True, rates=False, out=None):
+        """State read-back.  `out` may carry pre-allocated (e.g. pinned) arrays from a previous
+        call (the returned dict) to avoid re-allocating the result buffers."""
         nt, C_ = self.n_traj, self.n_carriers
-        out = {'n_steps': np.zeros(nt, dtype=np.int64), 'time': np.zeros(nt),
-               'occupancy': np.zeros((nt, C_), dtype=np.int32), 'drift': np.zeros((nt, C_, 3)),
-               'near_tie': np.zeros(nt, dtype=np.int64), 'clamped': np.zeros(nt, dtype=np.int64)}
-        uw = np.empty((nt, self.n_path, 3 * C_)) if (unwrapped and self.record_unwrapped) else None
-        rt = np.empty((nt, self.n_proc)) if rates else None
+        if out is None:
+            out = {'n_steps': np.zeros(nt, dtype=np.int64), 'time': np.zeros(nt),
+                   'occupancy': np.zeros((nt, C_), dtype=np.int32), 'drift': np.zeros((nt, C_, 3)),
+                   'near_tie': np.zeros(nt, dtype=np.int64), 'clamped': np.zeros(nt, dtype=np.int64),
+                   'unwrapped': None, 'rates': None}
+        uw = None
+        if unwrapped and self.record_unwrapped:
+            uw = out.get('unwrapped')
+            if uw is None:
+                uw = np.empty((nt, self.n_path, 3 * C_))
+        rt = None
+        if rates:
+            rt = out.get('rates')
+            if rt is None:
+                rt = np.empty((nt, self.n_proc))
         nat.check(nat.lib().pycd_kmc_read(self.handle, nat.ptr(uw), nat.ptr(out['n_steps']),
                                           nat.ptr(out['time']), nat.ptr(out['occupancy']),
                                           nat.ptr(out['drift']), nat.ptr(out['near_tie']),
@@ -293,6 +305,15 @@ class KmcEnsemble:
         out['unwrapped'] = uw
         out['rates'] = rt
         return out
+
+    def pinned_buffers(self):
+        """Result buffers in page-locked host memory, to be passed as read(out=...)."""
+        nt, C_ = self.n_traj, self.n_carriers
+        return {'n_steps': nat.pinned_empty(nt, np.int64), 'time': nat.pinned_empty(nt),
+                'occupancy': nat.pinned_empty((nt, C_), np.int32), 'drift': nat.pinned_empty((nt, C_, 3)),
+                'near_tie': nat.pinned_empty(nt, np.int64), 'clamped': nat.pinned_empty(nt, np.int64),
+                'unwrapped': nat.pinned_empty((nt, self.n_path, 3 * C_)) if self.record_unwrapped else None,
+                'rates': None}
 
     def unwrapped_device_ptr(self):
         p = C.c_void_p()
