@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument('--size', type=int, nargs=3, default=[10, 10, 10])
     ap.add_argument('--carriers', type=int, default=64)
     ap.add_argument('--traj-per-gpu', type=int, default=512)
-    ap.add_argument('--kmc-steps', type=int, default=2048, help='KMC steps per trajectory per bench step')
+    ap.add_argument('--kmc-steps', type=int, default=4096, help='KMC steps per trajectory per bench step')
     ap.add_argument('--refresh', type=int, default=64,
                     help='1 = stateless rate evaluation; R>1 = incremental updates, full re-gather every R')
     ap.add_argument('--n-path', type=int, default=101, help='rows of the recorded time grid')
@@ -267,7 +267,7 @@ def main():
     dt_grid = (total_kmc / (C_ * 3.2e9) * constants.SEC2AUTIME) / max(args.n_path - 1, 1)
     S = args.kmc_steps - (args.kmc_steps % args.refresh if args.refresh > 1 else 0)
 
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.int64, device=dev)   # 512 MB > 126 MB L2
 
     def barrier():
         torch.cuda.synchronize()
