@@ -267,7 +267,6 @@ def main():
     dt_grid = (total_kmc / (C_ * 3.2e9) * constants.SEC2AUTIME) / max(args.n_path - 1, 1)
     S = args.kmc_steps - (args.kmc_steps % args.refresh if args.refresh > 1 else 0)
 
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.int64, device=dev)   # 512 MB > 126 MB L2
 
     def barrier():
         torch.cuda.synchronize()
@@ -288,8 +287,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(steps):
             if not args.no_flush:
-                flush.zero_()             # L2 flush: 512 MB write between timed iterations
-                torch.cuda.synchronize()
+                ctx.flush_l2()            # 512 MB memset between timed iterations
             ens.advance_resident(S)
         barrier()
         wall = time.perf_counter() - t0

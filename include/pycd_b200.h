@@ -53,6 +53,8 @@ double pycd_ctx_last_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
 double pycd_ctx_total_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
 int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t kernel_class);
 int pycd_ctx_reset_timers(pycd_ctx *ctx);
+/* evict the L2 (512 MB memset on the context's stream); for cold-cache timing */
+int pycd_ctx_flush_l2(pycd_ctx *ctx);
 
 /* Page-locked host buffers for the end-to-end path (host numpy views over them make the
  * H2D/D2H copies of a call run at PCIe speed instead of through pageable staging). */

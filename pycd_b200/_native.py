@@ -106,6 +106,7 @@ _SIGNATURES = {
     'pycd_ctx_total_kernel_ms': (C.c_double, [C.c_void_p, C.c_int32]),
     'pycd_ctx_class_launches': (C.c_int64, [C.c_void_p, C.c_int32]),
     'pycd_ctx_reset_timers': (C.c_int, [C.c_void_p]),
+    'pycd_ctx_flush_l2': (C.c_int, [C.c_void_p]),
     'pycd_host_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     'pycd_host_free': (C.c_int, [C.c_void_p]),
     'pycd_ewald_rows': (C.c_int, [C.c_void_p, C.POINTER(EwaldDesc), C.c_int64, C.c_int64,
@@ -224,6 +225,9 @@ class Context:
 
     def reset_timers(self):
         check(lib().pycd_ctx_reset_timers(self.handle))
+
+    def flush_l2(self):
+        check(lib().pycd_ctx_flush_l2(self.handle))
 
 
 _default_ctx = {}

@@ -47,6 +47,8 @@ struct pycd_ctx {
     double last_ms[pycd::KC_COUNT] = {0, 0, 0, 0, 0, 0};
     double total_ms[pycd::KC_COUNT] = {0, 0, 0, 0, 0, 0};
     int64_t class_launches[pycd::KC_COUNT] = {0, 0, 0, 0, 0, 0};
+    void *flush_buf = nullptr;
+    int flush_value = 0;
 };
 
 namespace pycd {

@@ -69,6 +69,7 @@ int pycd_ctx_destroy(pycd_ctx *ctx) {
         for (int k = 0; k < KC_COUNT; ++k)
             for (int j = 0; j < 2; ++j)
                 if (ctx->ev[k][j]) cudaEventDestroy(ctx->ev[k][j]);
+        if (ctx->flush_buf) cudaFree(ctx->flush_buf);
         cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -98,6 +99,18 @@ double pycd_ctx_total_kernel_ms(pycd_ctx *ctx, int32_t k) {
 
 int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t k) {
     return (ctx && k >= 0 && k < KC_COUNT) ? ctx->class_launches[k] : -1;
+}
+
+int pycd_ctx_flush_l2(pycd_ctx *ctx) {
+    return guarded([&] {
+        PYCD_REQUIRE(ctx != nullptr, "ctx is NULL");
+        DeviceGuard g(ctx);
+        const size_t bytes = (size_t)512 << 20;  // 4x the 126 MB L2
+        if (!ctx->flush_buf) PYCD_CUDA(cudaMalloc(&ctx->flush_buf, bytes));
+        ctx->flush_value ^= 0xff;
+        PYCD_CUDA(cudaMemsetAsync(ctx->flush_buf, ctx->flush_value, bytes, ctx->stream));
+        PYCD_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
 }
 
 int pycd_host_alloc(int64_t bytes, void **out) {

@@ -111,24 +111,52 @@ __device__ __forceinline__ Site make_site(const SysDev &S, int idx)
     return s;
 }
 
+// Unpacked form of a site for the compact layout (one PRMT per field).
+struct USite {
+    int idx;         // dense: site index
+    int x, y, z, b;  // compact: cell coordinates and basis index
+};
+
+template <bool COMPACT>
+__device__ __forceinline__ USite unpack(const Site s)
+{
+    USite u;
+    u.idx = s.idx;
+    if (COMPACT) {
+        u.b = (int)__byte_perm(s.pack, 0u, 0x4440);
+        u.x = (int)__byte_perm(s.pack, 0u, 0x4441);
+        u.y = (int)__byte_perm(s.pack, 0u, 0x4442);
+        u.z = (int)__byte_perm(s.pack, 0u, 0x4443);
+    } else {
+        u.x = u.y = u.z = u.b = 0;
+    }
+    return u;
+}
+
 // P[x, y].  Dense: one 8-byte gather from the N x N array.  Compact: translation symmetry,
 // P[x,y] = Pu[basis_x][(cell_y - cell_x mod size)*n_basis + basis_y]; Pu (n_basis*N*8 bytes,
-// 7.2 MB at N = 30 000) stays L2-resident.
+// 7.2 MB at N = 30 000) stays L2-resident.  (d mod s) for d in (-s, s) is
+// min_unsigned(d, d + s): no predicates.
 template <bool COMPACT>
-__device__ __forceinline__ double ld_pair(const SysDev &S, const Site x, const Site y)
+__device__ __forceinline__ double ld_pair(const SysDev &S, const USite x, const USite y)
 {
     if (!COMPACT) {
         return __ldg(S.P + (long long)x.idx * S.n_sites + y.idx);
     } else {
-        int dx = (int)((y.pack >> 8) & 255u) - (int)((x.pack >> 8) & 255u);
-        int dy = (int)((y.pack >> 16) & 255u) - (int)((x.pack >> 16) & 255u);
-        int dz = (int)(y.pack >> 24) - (int)(x.pack >> 24);
-        dx += dx < 0 ? S.sx : 0;
-        dy += dy < 0 ? S.sy : 0;
-        dz += dz < 0 ? S.sz : 0;
-        const int col = ((dx * S.sy + dy) * S.sz + dz) * S.n_basis + (int)(y.pack & 255u);
-        return __ldg(S.P + (long long)(x.pack & 255u) * S.n_sites + col);
+        const int dx = y.x - x.x, dy = y.y - x.y, dz = y.z - x.z;
+        const unsigned wx = min((unsigned)dx, (unsigned)(dx + S.sx));
+        const unsigned wy = min((unsigned)dy, (unsigned)(dy + S.sy));
+        const unsigned wz = min((unsigned)dz, (unsigned)(dz + S.sz));
+        const unsigned col = ((wx * (unsigned)S.sy + wy) * (unsigned)S.sz + wz) * (unsigned)S.n_basis + (unsigned)y.b;
+        const unsigned off = (unsigned)x.b * (unsigned)S.n_sites + col;
+        return __ldg(S.P + off);
     }
+}
+
+template <bool COMPACT>
+__device__ __forceinline__ double ld_pair(const SysDev &S, const Site x, const Site y)
+{
+    return ld_pair<COMPACT>(S, unpack<COMPACT>(x), unpack<COMPACT>(y));
 }
 
 template <bool COMPACT>
@@ -217,7 +245,7 @@ __device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ
     a.pack = COMPACT ? s_occp[c] : 0u;
     const ProcStatic ps = load_process_static<COMPACT>(S, nn, p - c * nn, a, s_occe[c], fld, field_active);
     store_process_static<COMPACT>(M, p, ps);
-    const Site b = ps.b;
+    const USite ua = unpack<COMPACT>(a), ub = unpack<COMPACT>(ps.b);
     double t01 = ps.vl;
     for (int c0 = 0; c0 < C; c0 += GB) {
         double pb[GB], pa[GB];
@@ -227,8 +255,9 @@ __device__ __forceinline__ void gather_process(const SysDev &S, const int *s_occ
             Site sc;
             sc.idx = s_occ[c2];
             sc.pack = COMPACT ? s_occp[c2] : 0u;
-            pb[j] = ld_pair<COMPACT>(S, b, sc);
-            pa[j] = ld_pair<COMPACT>(S, a, sc);
+            const USite usc = unpack<COMPACT>(sc);
+            pb[j] = ld_pair<COMPACT>(S, ub, usc);
+            pa[j] = ld_pair<COMPACT>(S, ua, usc);
         }
 #pragma unroll
         for (int j = 0; j < GB; ++j)
@@ -255,6 +284,8 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     const int C = CT ? CT : E.C;
     const int nn = NNT ? NNT : S.nn;
     const int n_proc = (CT && NNT) ? CT * NNT : E.n_proc;
+    // fully specialised shape: one process and one (slot, carrier) item per thread
+    constexpr bool FAST = (CT > 0 && NNT > 0 && CT * NNT == BS && CT % 32 == 0);
     constexpr int NW = BS / 32;
     const int lane = tid & 31, wid = tid >> 5;
 
@@ -459,50 +490,83 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         a_old.pack = COMPACT ? M.ap[sel] : 0u;
         b_new.pack = COMPACT ? M.bp[sel] : 0u;
         const int e_new = M.be[sel];
+        const USite u_old = unpack<COMPACT>(a_old), u_new = unpack<COMPACT>(b_new);
         const bool next_full = (to_refresh == 0);
 
         // ---- issue the long-latency loads of this step's tail first ----
         double hv0 = 0.0, hv1 = 0.0, hv2 = 0.0;
-        if (tid == 0) {  // hop vector of the selected process (consumed after barrier C)
+        if (tid == 0) {  // hop vector of the selected process
             const double *hv = S.hopvec + ((long long)s_occe[cs] * nn + slot) * 3;
             hv0 = __ldg(hv); hv1 = __ldg(hv + 1); hv2 = __ldg(hv + 2);
         }
         double patch[4];
         int npatch = 0;
         ProcStatic moved;
-        const int my_slot = wid + lane * NW;   // lane j of warp w <-> slot w + j*NW of the moved carrier
-        const bool has_slot = !next_full && my_slot < nn;
         if (!next_full) {
-            // (a) untouched processes: 4 elements each
-            for (int p = tid; p < n_proc && npatch < 4; p += BS) {
-                double v = 0.0;
-                if (p / nn != cs) {
+            if constexpr (FAST) {
+                // one process and one (slot, carrier) item per thread; the moved carrier's own
+                // threads have no patch and prefetch their new process instead
+                if (tid / NNT != cs) {
                     Site pa, pb;
-                    pa.idx = M.a[p]; pb.idx = M.b[p];
-                    pa.pack = COMPACT ? M.ap[p] : 0u;
-                    pb.pack = COMPACT ? M.bp[p] : 0u;
-                    const double nb_ = ld_pair<COMPACT>(S, pb, b_new), na_ = ld_pair<COMPACT>(S, pa, b_new);
-                    const double ob_ = ld_pair<COMPACT>(S, pb, a_old), oa_ = ld_pair<COMPACT>(S, pa, a_old);
-                    v = S.qc * (nb_ - na_) - S.qc * (ob_ - oa_);
+                    pa.idx = M.a[tid]; pb.idx = M.b[tid];
+                    pa.pack = COMPACT ? M.ap[tid] : 0u;
+                    pb.pack = COMPACT ? M.bp[tid] : 0u;
+                    const USite ua = unpack<COMPACT>(pa), ub = unpack<COMPACT>(pb);
+                    const double nb_ = ld_pair<COMPACT>(S, ub, u_new), na_ = ld_pair<COMPACT>(S, ua, u_new);
+                    const double ob_ = ld_pair<COMPACT>(S, ub, u_old), oa_ = ld_pair<COMPACT>(S, ua, u_old);
+                    patch[0] = S.qc * (nb_ - na_) - S.qc * (ob_ - oa_);
+                } else {
+                    moved = load_process_static<COMPACT>(S, nn, tid % NNT, b_new, e_new, fld, field_active);
                 }
-                patch[npatch++] = v;
-            }
-            // (b) the moved carrier's nn processes: (slot, carrier) items over the whole block
-            for (int item = tid; item < nn * C; item += BS) {
-                const int sl = item / C, c2 = item - sl * C;
+                const int sl = tid / CT, c2 = tid % CT;   // warp-uniform slot (CT % 32 == 0)
                 Site nbr;
                 nbr.idx = __ldg(S.neigh + (long long)e_new * nn + sl);
                 nbr.pack = COMPACT ? __ldg(S.neigh_pack + (long long)e_new * nn + sl) : 0u;
                 Site sc;
                 if (c2 == cs) sc = b_new;
                 else { sc.idx = s_occ[c2]; sc.pack = COMPACT ? s_occp[c2] : 0u; }
-                s_terms[item] = S.qc * (ld_pair<COMPACT>(S, nbr, sc) - ld_pair<COMPACT>(S, b_new, sc));
+                const USite usc = unpack<COMPACT>(sc);
+                double term = S.qc * (ld_pair<COMPACT>(S, unpack<COMPACT>(nbr), usc) - ld_pair<COMPACT>(S, u_new, usc));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+                if (lane == 0) s_terms[wid] = term;   // CT/32 partial sums per slot
+            } else {
+                // (a) untouched processes: 4 elements each
+                for (int p = tid; p < n_proc && npatch < 4; p += BS) {
+                    double v = 0.0;
+                    if (p / nn != cs) {
+                        Site pa, pb;
+                        pa.idx = M.a[p]; pb.idx = M.b[p];
+                        pa.pack = COMPACT ? M.ap[p] : 0u;
+                        pb.pack = COMPACT ? M.bp[p] : 0u;
+                        const USite ua = unpack<COMPACT>(pa), ub = unpack<COMPACT>(pb);
+                        const double nb_ = ld_pair<COMPACT>(S, ub, u_new), na_ = ld_pair<COMPACT>(S, ua, u_new);
+                        const double ob_ = ld_pair<COMPACT>(S, ub, u_old), oa_ = ld_pair<COMPACT>(S, ua, u_old);
+                        v = S.qc * (nb_ - na_) - S.qc * (ob_ - oa_);
+                    }
+                    patch[npatch++] = v;
+                }
+                // (b) the moved carrier's nn processes: (slot, carrier) items over the whole block
+                for (int item = tid; item < nn * C; item += BS) {
+                    const int sl = item / C, c2 = item - sl * C;
+                    Site nbr;
+                    nbr.idx = __ldg(S.neigh + (long long)e_new * nn + sl);
+                    nbr.pack = COMPACT ? __ldg(S.neigh_pack + (long long)e_new * nn + sl) : 0u;
+                    Site sc;
+                    if (c2 == cs) sc = b_new;
+                    else { sc.idx = s_occ[c2]; sc.pack = COMPACT ? s_occp[c2] : 0u; }
+                    const USite usc = unpack<COMPACT>(sc);
+                    s_terms[item] = S.qc * (ld_pair<COMPACT>(S, unpack<COMPACT>(nbr), usc) -
+                                            ld_pair<COMPACT>(S, u_new, usc));
+                }
+                // (c) static parts of the moved carrier's new processes: lane j of warp w <-> slot w + j*NW
+                const int my_slot = wid + lane * NW;
+                if (my_slot < nn)
+                    moved = load_process_static<COMPACT>(S, nn, my_slot, b_new, e_new, fld, field_active);
             }
-            // (c) static parts of the moved carrier's new processes
-            if (has_slot) moved = load_process_static<COMPACT>(S, nn, my_slot, b_new, e_new, fld, field_active);
         }
 
-        // ---- thread 0: time advance, grid bookkeeping, core.py:2802-2804, 2848-2861 ----
+        // ---- thread 0: time advance, grid bookkeeping, hop, core.py:2802-2830, 2844-2861 ----
         if (tid == 0) {
             t += nlog_u2 / ktot;
             const long long end = (long long)(t / E.dt_grid);
@@ -516,13 +580,10 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             if (E.stop_at_grid_end && end >= E.n_path) ctl.fin = 1;
             if (E.step_limit > 0 && steps_total + step_local + 1 >= E.step_limit) ctl.fin = 1;
             s_ctl[par] = ctl;
-        }
-        // ---- next step's draws (off the critical path: the block is waiting on gathers) ----
-        if (tid == rng_tid) draw(step_local + 1, s_u + 2 * (par ^ 1));
-        __syncthreads();  // (C) s_terms, s_ctl visible; everyone is done with s_occ[cs] / M.*[sel]
-
-        // ---- bring the cached sums up to date for the next step ----
-        if (tid == 0) {  // core.py:2810-2830, 2844-2845
+            // the other threads only read the entries of the carriers that did not move
+            s_occ[cs] = b_new.idx;
+            s_occe[cs] = e_new;
+            if (COMPACT) s_occp[cs] = b_new.pack;
             const double kp = M.k[sel];
             s_disp[3 * cs] += hv0; s_disp[3 * cs + 1] += hv1; s_disp[3 * cs + 2] += hv2;
             if (field_active) {
@@ -530,41 +591,59 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             }
             if (A.events_out) A.events_out[(long long)traj * A.max_steps + step_local] = sel;
             if (A.times_out) A.times_out[(long long)traj * A.max_steps + step_local] = t;
-            s_occ[cs] = b_new.idx;
-            s_occe[cs] = e_new;
-            if (COMPACT) s_occp[cs] = b_new.pack;
         }
+        // ---- next step's draws (off the critical path: the block is waiting on gathers) ----
+        if (tid == rng_tid) draw(step_local + 1, s_u + 2 * (par ^ 1));
+        __syncthreads();  // (C) s_terms, s_ctl, s_occ, s_disp visible; all reads of M.*[sel] done
+
+        // ---- bring the cached sums up to date for the next step ----
         if (!next_full) {
-            int ip = 0;
-            for (int p = tid; p < n_proc; p += BS, ++ip) {
-                if (p / nn == cs) continue;
-                if (ip < 4) {
-                    M.t01[p] += patch[ip];
+            if constexpr (FAST) {
+                if (tid / NNT != cs) {
+                    M.t01[tid] += patch[0];
                 } else {
-                    Site pa, pb;
-                    pa.idx = M.a[p]; pb.idx = M.b[p];
-                    pa.pack = COMPACT ? M.ap[p] : 0u;
-                    pb.pack = COMPACT ? M.bp[p] : 0u;
-                    M.t01[p] += S.qc * (ld_pair<COMPACT>(S, pb, b_new) - ld_pair<COMPACT>(S, pa, b_new)) -
-                                S.qc * (ld_pair<COMPACT>(S, pb, a_old) - ld_pair<COMPACT>(S, pa, a_old));
-                }
-            }
-            // one warp per slot of the moved carrier: reduce its C contributions
-            int j = 0;
-            for (int sl = wid; sl < nn; sl += NW, ++j) {
-                double acc = 0.0;
-                for (int c2 = lane; c2 < C; c2 += 32) acc += s_terms[sl * C + c2];
+                    constexpr int PARTS = CT / 32;
+                    const int sl = tid % NNT;
+                    double acc = 0.0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == j) {
-                    const int p = cs * nn + sl;
-                    store_process_static<COMPACT>(M, p, moved);
-                    M.t01[p] = moved.vl + acc;
+                    for (int j = 0; j < PARTS; ++j) acc += s_terms[sl * PARTS + j];
+                    store_process_static<COMPACT>(M, tid, moved);
+                    M.t01[tid] = moved.vl + acc;
+                }
+            } else {
+                int ip = 0;
+                for (int p = tid; p < n_proc; p += BS, ++ip) {
+                    if (p / nn == cs) continue;
+                    if (ip < 4) {
+                        M.t01[p] += patch[ip];
+                    } else {
+                        Site pa, pb;
+                        pa.idx = M.a[p]; pb.idx = M.b[p];
+                        pa.pack = COMPACT ? M.ap[p] : 0u;
+                        pb.pack = COMPACT ? M.bp[p] : 0u;
+                        const USite ua = unpack<COMPACT>(pa), ub = unpack<COMPACT>(pb);
+                        M.t01[p] += S.qc * (ld_pair<COMPACT>(S, ub, u_new) - ld_pair<COMPACT>(S, ua, u_new)) -
+                                    S.qc * (ld_pair<COMPACT>(S, ub, u_old) - ld_pair<COMPACT>(S, ua, u_old));
+                    }
+                }
+                // one warp per slot of the moved carrier: reduce its C contributions
+                int j = 0;
+                for (int sl = wid; sl < nn; sl += NW, ++j) {
+                    double acc = 0.0;
+                    for (int c2 = lane; c2 < C; c2 += 32) acc += s_terms[sl * C + c2];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == j) {
+                        const int p = cs * nn + sl;
+                        store_process_static<COMPACT>(M, p, moved);
+                        M.t01[p] = moved.vl + acc;
+                    }
                 }
             }
         }
         ++step_local;
-        __syncthreads();  // (D)
+        // (D) only the generic incremental path hands entries of M.* to non-owner threads
+        if (!FAST && !next_full) __syncthreads();
     }
 
     // ---- write the state back ----
