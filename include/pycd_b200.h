@@ -160,6 +160,8 @@ typedef struct {
     const double *kT_traj;     /* NULL or (n_traj): per-trajectory temperature (sweeps) */
     const double *field_traj;  /* NULL or (n_traj,3): per-trajectory field (implies field_active) */
     int32_t record_unwrapped;  /* 1: keep the (n_traj, n_path, 3C) displacement grid on the device */
+    const double *energy0;     /* NULL, or (n_traj) system energy of the initial state (core.py:2778-2780):
+                                  turns on the energy / delg_0 grids of output_data */
 } pycd_kmc_ensemble_desc;
 
 int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ensemble_desc *desc,
@@ -186,6 +188,8 @@ int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *dr
 int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t *n_steps, double *sim_time,
                   int32_t *occupancy, double *drift, int64_t *near_tie, int64_t *clamped,
                   double *rates /* (n_traj, C*nn) rates of the last evaluated step */);
+/* output_data 'energy' and 'delg_0' (core.py:2807-2809, 2855-2857): (n_traj, n_path) each; either may be NULL */
+int pycd_kmc_read_energy(pycd_kmc_ensemble *ens, double *energy_grid, double *dg0_grid);
 /* device pointer of the resident displacement grid (input of pycd_msd without a copy) */
 int pycd_kmc_unwrapped_device(pycd_kmc_ensemble *ens, const double **dev_ptr);
 

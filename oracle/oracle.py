@@ -58,7 +58,8 @@ def lib():
         h.oracle_kmc_trajectory.restype = C.c_int64
         h.oracle_kmc_trajectory.argtypes = [C.POINTER(KmcParams), C.c_uint64, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_double, C.c_void_p, C.c_void_p]
         h.oracle_kmc_ensemble.restype = C.c_int64
         h.oracle_kmc_ensemble.argtypes = [C.POINTER(KmcParams), C.c_int64, C.c_uint64, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -155,7 +156,8 @@ class KmcOracle:
         self.p = p
         self.n_proc = run.n_carriers * t.nn
 
-    def trajectory(self, occ, draws=None, traj_id=0, cap_steps=0, want_times=False, want_events=False):
+    def trajectory(self, occ, draws=None, traj_id=0, cap_steps=0, want_times=False, want_events=False,
+                   energy0=None):
         C_ = self.p.n_carriers
         occ = np.ascontiguousarray(occ, dtype=np.int32).copy()
         assert occ.shape == (C_,)
@@ -172,13 +174,17 @@ class KmcOracle:
         dg0 = np.zeros(self.n_proc)
         clamped = C.c_int64(0)
         energy = C.c_double(0.0)
+        e_grid = np.zeros(self.p.n_path) if energy0 is not None else None
+        g_grid = np.zeros(self.p.n_path) if energy0 is not None else None
         n = lib().oracle_kmc_trajectory(C.byref(self.p), int(traj_id), _p(occ), _p(draws), n_draw_steps,
                                         _p(uw), _p(times), _p(events), int(cap_steps), _p(drift),
-                                        _p(rates0), C.byref(clamped), C.byref(energy), _p(dg0))
+                                        _p(rates0), C.byref(clamped), C.byref(energy), _p(dg0),
+                                        float(energy0 or 0.0), _p(e_grid), _p(g_grid))
         return {'n_steps': int(n), 'occupancy': occ, 'unwrapped': uw,
                 'times': times[:n + 1] if want_times else None,
                 'events': events[:n] if want_events else None, 'drift': drift, 'rates0': rates0,
-                'dg0_first': dg0, 'clamped': clamped.value, 'energy_change': energy.value}
+                'dg0_first': dg0, 'clamped': clamped.value, 'energy_change': energy.value,
+                'energy_grid': e_grid, 'dg0_grid': g_grid}
 
     def ensemble(self, occ, traj_id0=0, draws=None, want_unwrapped=True, n_threads=0):
         C_ = self.p.n_carriers

@@ -89,7 +89,7 @@ class KmcEnsembleDesc(C.Structure):
                 ('step_limit', C.c_int64), ('stop_at_grid_end', C.c_int32),
                 ('rng_mode', C.c_int32), ('seed', C.c_uint64), ('refresh_interval', C.c_int32),
                 ('kT_traj', C.c_void_p), ('field_traj', C.c_void_p),
-                ('record_unwrapped', C.c_int32)]
+                ('record_unwrapped', C.c_int32), ('energy0', C.c_void_p)]
 
 
 _lib = None
@@ -124,6 +124,7 @@ _SIGNATURES = {
     'pycd_kmc_advance': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.POINTER(C.c_int64)]),
     'pycd_kmc_read': (C.c_int, [C.c_void_p] + [C.c_void_p] * 8),
+    'pycd_kmc_read_energy': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pycd_kmc_unwrapped_device': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'pycd_msd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                            C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

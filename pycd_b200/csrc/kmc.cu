@@ -54,6 +54,9 @@ struct EnsDev {
     const double *kT_traj;
     const double *field_traj;
     double *unwrapped;     // [n_traj][n_path][3C] or NULL
+    double *energy;        // [n_traj] current_state_energy, or NULL (energy outputs off)
+    double *energy_grid;   // [n_traj][n_path]
+    double *dg0_grid;      // [n_traj][n_path]
     double dt_grid;
     long long n_path;
     long long step_limit;
@@ -370,6 +373,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     }
     // thread-0 scalars
     double t = E.t[traj];
+    double energy = (E.energy && tid == 0) ? E.energy[traj] : 0.0;
     long long start = E.start_idx[traj];
     long long n_tie = 0, n_clamp = 0;
     long long step_local = 0;
@@ -570,12 +574,20 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         if (tid == 0) {
             t += nlog_u2 / ktot;
             const long long end = (long long)(t / E.dt_grid);
+            const long long start_before = start;
             StepCtl ctl;
             ctl.r0 = 0; ctl.r1 = 0; ctl.fin = 0; ctl.pad = 0;
             if (end >= start + 1) {
                 const long long e2 = end >= E.n_path ? E.n_path : end;
                 if (start < E.n_path) { ctl.r0 = start; ctl.r1 = e2; }
                 start = e2;
+            }
+            if (E.energy) {  // output_data energy / delg_0, core.py:2807-2809, 2826, 2855-2857
+                const double g0 = __dadd_rn(__dmul_rn(two_qc, __dadd_rn(M.t01[sel], M.t02[sel])), M.shift[sel]);
+                const long long lo_r = start_before, hi_r = end < E.n_path ? end : E.n_path;
+                for (long long r = lo_r; r < hi_r; ++r) E.dg0_grid[(long long)traj * E.n_path + r] = g0;
+                energy += g0;
+                for (long long r = ctl.r0; r < ctl.r1; ++r) E.energy_grid[(long long)traj * E.n_path + r] = energy;
             }
             if (E.stop_at_grid_end && end >= E.n_path) ctl.fin = 1;
             if (E.step_limit > 0 && steps_total + step_local + 1 >= E.step_limit) ctl.fin = 1;
@@ -658,6 +670,7 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         for (int p = tid; p < n_proc; p += BS) E.rates[(long long)traj * n_proc + p] = M.k[p];
     if (tid == 0) {
         E.t[traj] = t;
+        if (E.energy) E.energy[traj] = energy;
         E.start_idx[traj] = start;
         E.n_steps[traj] = steps_total + step_local;
         E.near_tie[traj] += n_tie;
@@ -740,9 +753,13 @@ struct pycd_kmc_ensemble {
     pycd_kmc_system *sys = nullptr;
     EnsDev dev{};
     DevBuf<int> occ, done;
-    DevBuf<double> t, disp, row, drift, rates, unwrapped, kT_traj, field_traj;
+    DevBuf<double> t, disp, row, drift, rates, unwrapped, kT_traj, field_traj, energy, energy_grid, dg0_grid;
+    std::vector<double> energy0;
     DevBuf<long long> start_idx, n_steps, near_tie, clamped;
 };
+
+// energy outputs at t = 0: energy_array[0] = initial energy, everything else 0 (core.py:2715-2718, 2782-2783)
+static void arm_energy(pycd_kmc_ensemble *ens, cudaStream_t s);
 
 extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc *d,
                                       pycd_kmc_system **out) {
@@ -888,6 +905,13 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
                 ens->unwrapped.alloc((size_t)nt * d->n_path * 3 * C);
                 ens->unwrapped.zero(s);
             }
+            if (d->energy0) {
+                ens->energy0.resize(nt);
+                PYCD_CUDA(cudaMemcpy(ens->energy0.data(), d->energy0, sizeof(double) * nt, cudaMemcpyDefault));
+                ens->energy.alloc(nt);
+                ens->energy_grid.alloc((size_t)nt * d->n_path);
+                ens->dg0_grid.alloc((size_t)nt * d->n_path);
+            }
             if (d->kT_traj) {
                 ens->kT_traj.alloc(nt);
                 PYCD_CUDA(cudaMemcpyAsync(ens->kT_traj.p, d->kT_traj, sizeof(double) * nt, cudaMemcpyDefault, s));
@@ -896,8 +920,11 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
                 ens->field_traj.alloc((size_t)nt * 3);
                 PYCD_CUDA(cudaMemcpyAsync(ens->field_traj.p, d->field_traj, sizeof(double) * nt * 3, cudaMemcpyDefault, s));
             }
-            PYCD_CUDA(cudaStreamSynchronize(s));
             EnsDev &e = ens->dev;
+            e.energy = ens->energy.p; e.energy_grid = ens->energy_grid.p; e.dg0_grid = ens->dg0_grid.p;
+            e.n_path = d->n_path;
+            arm_energy(ens, s);
+            PYCD_CUDA(cudaStreamSynchronize(s));
             e.C = C; e.n_proc = (int)n_proc_ll; e.n_traj = nt; e.traj_id0 = d->traj_id0;
             e.occ = ens->occ.p; e.t = ens->t.p; e.start_idx = ens->start_idx.p; e.done = ens->done.p;
             e.disp = ens->disp.p; e.row = ens->row.p; e.n_steps = ens->n_steps.p;
@@ -911,6 +938,30 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
             throw;
         }
         *out = ens;
+    });
+}
+
+static void arm_energy(pycd_kmc_ensemble *ens, cudaStream_t s) {
+    if (!ens->energy.p) return;
+    const size_t nt = ens->energy0.size();
+    const long long n_path = ens->dev.n_path;
+    ens->energy_grid.zero(s);
+    ens->dg0_grid.zero(s);
+    PYCD_CUDA(cudaMemcpyAsync(ens->energy.p, ens->energy0.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, s));
+    PYCD_CUDA(cudaMemcpy2DAsync(ens->energy_grid.p, sizeof(double) * n_path, ens->energy0.data(), sizeof(double),
+                                sizeof(double), nt, cudaMemcpyHostToDevice, s));
+}
+
+extern "C" int pycd_kmc_read_energy(pycd_kmc_ensemble *ens, double *energy_grid, double *dg0_grid) {
+    return guarded([&] {
+        PYCD_REQUIRE(ens, "NULL ensemble");
+        PYCD_REQUIRE(ens->energy.p, "ensemble was created without energy0");
+        DeviceGuard g(ens->sys->ctx);
+        cudaStream_t s = ens->sys->ctx->stream;
+        const size_t n = (size_t)ens->dev.n_traj * ens->dev.n_path;
+        if (energy_grid) PYCD_CUDA(cudaMemcpyAsync(energy_grid, ens->energy_grid.p, sizeof(double) * n, cudaMemcpyDefault, s));
+        if (dg0_grid) PYCD_CUDA(cudaMemcpyAsync(dg0_grid, ens->dg0_grid.p, sizeof(double) * n, cudaMemcpyDefault, s));
+        PYCD_CUDA(cudaStreamSynchronize(s));
     });
 }
 
@@ -929,6 +980,7 @@ extern "C" int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *oc
         std::vector<long long> ones(nt, 1);
         PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
         E.traj_id0 = traj_id0;
+        arm_energy(ens, s);
         PYCD_CUDA(cudaStreamSynchronize(s));
     });
 }

@@ -77,6 +77,19 @@ class RunParameters:
                 self.field = ef['mag'] * (direction / np.linalg.norm(direction))
                 self.field_active = 1
 
+    def initial_energy(self, P, occupancy, alpha_per_angstrom):
+        """current_state_energy before the first step (core.py:2663-2667, 2773-2780):
+        ewald_neut + sum_ij q_i q_j P_ij with q = lattice charges + carriers.  alpha is the
+        value material_run re-reads from precomputed_array.log (1/angstrom)."""
+        sc = self.supercell
+        alpha = alpha_per_angstrom / constants.ANG2BOHR  # core.py:768-769
+        system_charge = float(np.dot(self.species_count,
+                                     self.lattice.species_charge_list[self.species_charge_type]))
+        ewald_neut = -(np.pi * system_charge ** 2 / (2 * sc.system_volume * alpha))
+        q = self.q_lat.copy()
+        np.add.at(q, np.asarray(occupancy, dtype=int), self.q_carrier)
+        return ewald_neut + float(q @ (P @ q))
+
     # -- initial state -----------------------------------------------------------------
     def initial_occupancy_from(self, rng):
         """generate_initial_occupancy without doping (core.py:2483-2528): explicit sites
@@ -205,7 +218,7 @@ class KmcEnsemble:
 
     def __init__(self, system, occupancy0, dt_grid=None, n_path=None, step_limit=0,
                  stop_at_grid_end=True, rng_mode=nat.RNG_REPLAY, seed=0, traj_id0=0,
-                 refresh_interval=1, kT_traj=None, field_traj=None, record_unwrapped=True):
+                 refresh_interval=1, kT_traj=None, field_traj=None, record_unwrapped=True, energy0=None):
         run = system.run
         self.system = system
         occ = np.ascontiguousarray(occupancy0, dtype=np.int32)
@@ -238,6 +251,12 @@ class KmcEnsemble:
             assert field_traj.shape == (self.n_traj, 3)
             d.field_traj = nat.ptr(field_traj)
             keep.append(field_traj)
+        self.has_energy = energy0 is not None
+        if energy0 is not None:
+            energy0 = np.ascontiguousarray(energy0, dtype=np.float64)
+            assert energy0.shape == (self.n_traj,)
+            d.energy0 = nat.ptr(energy0)
+            keep.append(energy0)
         d.record_unwrapped = int(bool(record_unwrapped))
         self.record_unwrapped = bool(record_unwrapped)
         self._h = C.c_void_p()
@@ -315,6 +334,13 @@ class KmcEnsemble:
                 'unwrapped': nat.pinned_empty((nt, self.n_path, 3 * C_)) if self.record_unwrapped else None,
                 'rates': None}
 
+    def read_energy(self):
+        """(energy_traj, delG0_traj), each (n_traj, n_path) (output_data energy / delg_0)."""
+        e = np.empty((self.n_traj, self.n_path))
+        g = np.empty((self.n_traj, self.n_path))
+        nat.check(nat.lib().pycd_kmc_read_energy(self.handle, nat.ptr(e), nat.ptr(g)))
+        return e, g
+
     def unwrapped_device_ptr(self):
         p = C.c_void_p()
         nat.check(nat.lib().pycd_kmc_unwrapped_device(self.handle, C.byref(p)))
@@ -333,12 +359,12 @@ class KmcEnsemble:
 
 
 def run_replay(system, rngs, occupancy0, chunk_steps=32768, want_times=True, want_events=False,
-               max_total_steps=None):
+               max_total_steps=None, energy0=None):
     """Runs trajectories to the end of their time grid, feeding each one the continuing
     stream of its own Python MT19937 generator (u1 then u2 per step, core.py:2799-2802).
     Returns (state dict from KmcEnsemble.read, list of per-trajectory time arrays incl. the
     leading 0.0, list of per-trajectory event arrays or None)."""
-    ens = KmcEnsemble(system, occupancy0, rng_mode=nat.RNG_REPLAY, refresh_interval=1)
+    ens = KmcEnsemble(system, occupancy0, rng_mode=nat.RNG_REPLAY, refresh_interval=1, energy0=energy0)
     n_traj = ens.n_traj
     times = [[np.zeros(1)] for _ in range(n_traj)]
     events = [[] for _ in range(n_traj)]
@@ -363,6 +389,8 @@ def run_replay(system, rngs, occupancy0, chunk_steps=32768, want_times=True, wan
         if res['n_active'] == 0 or (max_total_steps and total >= max_total_steps):
             break
     state = ens.read()
+    if energy0 is not None:
+        state['energy_grid'], state['dg0_grid'] = ens.read_energy()
     ens.close()
     t_out = [np.concatenate(t) for t in times] if want_times else None
     e_out = [np.concatenate(e) if e else np.zeros(0, dtype=np.int32) for e in events] \

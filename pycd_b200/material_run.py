@@ -39,7 +39,7 @@ def material_run(dst_path):
         raise NotImplementedError('doping is outside the accelerated path (SURVEY section 2)')
     opts = sim['b200']
     hop = load_hop_neighbor_list(inp / 'hop_neighbor_list.npy')
-    _alpha_from_log(inp / 'precomputed_array.log', params.alpha)  # only feeds the energy output
+    alpha_log = _alpha_from_log(inp / 'precomputed_array.log', params.alpha)  # feeds the energy output only
     P = np.load(inp / 'precomputed_array.npy')
     parallel = sim['compute_mode'] == 'parallel'
     n_traj = 1 if parallel else int(sim['n_traj'])
@@ -48,9 +48,7 @@ def material_run(dst_path):
                             sim['species_count'], sim['initial_occupancy'],
                             sim['relative_energies'], sim['external_field'])
     out_cfg = sim['output_data']
-    for key in ('energy', 'delg_0'):
-        if out_cfg.get(key, {}).get('write'):
-            raise NotImplementedError(f"output_data['{key}'] is not produced by the accelerated path")
+    want_energy = bool(out_cfg.get('energy', {}).get('write') or out_cfg.get('delg_0', {}).get('write'))
     if out_cfg['unwrapped_traj'].get('write_every_step'):
         raise NotImplementedError('write_every_step is not supported (SURVEY appendix D)')
 
@@ -68,13 +66,17 @@ def material_run(dst_path):
     if rng_kind == 'replay':
         rngs = [kmc.load_rnd_state(d / 'initial_rnd_state.dump') for d in traj_dirs]
         occ = np.array([run.initial_occupancy_from(r) for r in rngs], dtype=np.int32)
-        state, times, _ = kmc.run_replay(system, rngs, occ, chunk_steps=chunk, want_times=want_times)
+        energy0 = np.array([run.initial_energy(P, o, alpha_log) for o in occ]) if want_energy else None
+        state, times, _ = kmc.run_replay(system, rngs, occ, chunk_steps=chunk, want_times=want_times,
+                                         energy0=energy0)
     elif rng_kind == 'philox':
         seed = int(sim['random_seed'])
         occ = kmc.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed)
         refresh = int(opts.get('refresh_interval', 1))
         chunk -= chunk % refresh
-        ens = kmc.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=seed, refresh_interval=refresh)
+        energy0 = np.array([run.initial_energy(P, o, alpha_log) for o in occ]) if want_energy else None
+        ens = kmc.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=seed, refresh_interval=refresh,
+                              energy0=energy0)
         pieces = [[np.zeros(1)] for _ in range(n_traj)]
         while True:
             res = ens.advance(chunk, want_times=want_times)
@@ -86,6 +88,8 @@ def material_run(dst_path):
             if res['n_active'] == 0:
                 break
         state = ens.read()
+        if want_energy:
+            state['energy_grid'], state['dg0_grid'] = ens.read_energy()
         ens.close()
         times = [np.concatenate(p) for p in pieces] if want_times else None
     else:
@@ -102,6 +106,10 @@ def material_run(dst_path):
                 np.save(target, state['unwrapped'][i])
             elif kind == 'time':
                 np.save(target, times[i])
+            elif kind == 'energy':
+                np.save(target, state['energy_grid'][i])
+            elif kind == 'delg_0':
+                np.save(target, state['dg0_grid'][i])
             elif kind == 'wrapped_traj':  # allocated, never filled by the reference (core.py:2712-2714)
                 np.save(target, np.zeros((n_path, c3)))
             elif kind == 'potential':     # likewise (core.py:2719-2721)

@@ -107,6 +107,9 @@ def reference_case(tag, example, species_count, extra, with_msd=False):
         out[f'time_index_{i}'] = idx
         out[f'time_value_{i}'] = td[idx]
         total_steps += len(td) - 1
+        for key, fname in (('energy', 'energy_traj.npy'), ('delg0', 'delG0_traj.npy')):
+            if (d / fname).exists():
+                out[f'{key}_{i}'] = np.load(d / fname)
     if (work / 'drift_mobility.dat').exists():
         out['drift_mobility'] = np.loadtxt(work / 'drift_mobility.dat', ndmin=2)
     # first-step rates from the reference's own rate routine
@@ -147,10 +150,20 @@ def shipped_msd(example):
     print(f'msd {example}:', sorted(work.glob('MSD_Analysis_*.log'))[0].read_text().splitlines()[:2])
 
 
+def energy_case():
+    """energy_traj.npy / delG0_traj.npy of the reference (output_data energy / delg_0 on)."""
+    reference_case('hematite_4e_energy', 'Hematite', [4, 0],
+                   {'random_seed': 11, 't_final': 2.0e-6, 'n_traj': 1,
+                    'output_data': {'energy': {'write': 1}, 'delg_0': {'write': 1}}})
+
+
 def main():
     if not rh.reference_available():
         raise SystemExit('reference not available; golden vectors are already committed')
     TMP.mkdir(exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'energy':
+        energy_case()
+        return
     copy_example('Hematite')
     copy_example('BVO')
     shipped_msd('Hematite')
@@ -162,6 +175,7 @@ def main():
                    dict(field_on, random_seed=7, t_final=2.0e-7, time_interval=1.0e-9, n_traj=2))
     reference_case('bvo_4e', 'BVO', [4, 0], {'random_seed': 2, 't_final': 3.0e-4, 'n_traj': 1})
     reference_case('bvo_2h', 'BVO', [0, 2], {'random_seed': 5, 't_final': 2.0e-6, 'n_traj': 1})
+    energy_case()
 
 
 if __name__ == '__main__':

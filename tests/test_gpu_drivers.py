@@ -117,3 +117,22 @@ def test_setup_generates_loadable_neighbour_list_and_philox_run(tmp_path):
         td = np.load(work / f'traj{i + 1}' / 'time_data.npy')
         assert uw.shape == (201, 9) and np.all(uw[0] == 0) and np.any(uw[-1] != 0)
         assert td[0] == 0.0 and np.all(np.diff(td) > 0) and td[-1] >= 2.0e-6 * 4.134137336634339e16
+
+
+def test_energy_and_delg0_outputs(tmp_path):
+    """output_data energy / delg_0 files equal the reference run's energy_traj.npy / delG0_traj.npy."""
+    from pycd_b200 import material_run
+    ex, z = H.load_ref_case('hematite_4e_energy')
+    work = _stage('hematite', tmp_path)
+    yaml.safe_dump(yaml.safe_load(str(z['sim_yaml'])), open(work / 'simulation_parameters.yml', 'w'))
+    from pycd_b200 import ewald as EW
+    from datetime import datetime
+    from pycd_b200.fileio import generate_report
+    generate_report(datetime.now(), work / 'InputFiles', 'precomputed_array', 1,
+                    ''.join(EW.log_prefix(H.ewald_parameters(ex))))
+    material_run(work)
+    assert np.array_equal(np.load(work / 'traj1' / 'unwrapped_traj.npy'), z['unwrapped_0'])
+    assert np.allclose(np.load(work / 'traj1' / 'energy_traj.npy'), z['energy_0'], rtol=1e-12, atol=0)
+    dg = np.load(work / 'traj1' / 'delG0_traj.npy')
+    assert np.allclose(dg, z['delg0_0'], rtol=1e-9, atol=1e-15)
+    assert np.array_equal(dg == 0, z['delg0_0'] == 0)

@@ -80,6 +80,23 @@ def test_reference_generated_cases(tag, literal):
             assert np.allclose(mob, z['drift_mobility'][i], rtol=1e-11)
 
 
+@pytest.mark.parametrize('literal', [False, True])
+def test_energy_and_delg0_outputs(literal):
+    """output_data energy / delg_0 (core.py:2782-2783, 2807-2809, 2826, 2855-2857)."""
+    ex, z = H.load_ref_case('hematite_4e_energy')
+    run = H.run_parameters(ex)
+    rng = H.rng_from_state_bytes(z['rnd_state_0'])
+    occ = run.initial_occupancy_from(rng)
+    n_events = int(z['time_n_0']) - 1
+    e0 = run.initial_energy(ex.P, occ, 0.2667)
+    assert abs(e0 - z['energy_0'][0]) <= 1e-12 * abs(e0)
+    res = O.KmcOracle(run, ex.P, literal=literal).trajectory(occ, H.draw_stream(rng, n_events + 8), energy0=e0)
+    assert res['n_steps'] == n_events
+    assert np.allclose(res['energy_grid'], z['energy_0'], rtol=1e-12, atol=0)
+    assert np.allclose(res['dg0_grid'], z['delg0_0'], rtol=1e-9, atol=1e-15)
+    assert np.array_equal(res['dg0_grid'] == 0, z['delg0_0'] == 0)
+
+
 def test_gather_identity_equals_literal_rates():
     ex, z = H.load_ref_case('hematite_4e')
     run = H.run_parameters(ex)
