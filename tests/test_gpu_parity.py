@@ -210,6 +210,53 @@ def test_unit_rows_layout_matches_oracle_on_expanded_array(ctx, case, refresh):
     assert np.array_equal(again['unwrapped'], got['unwrapped'])
 
 
+@pytest.mark.parametrize('refresh,chunk', [(1, 500), (8, 512)])
+def test_time_grid_mode_chunked_launches(ctx, refresh, chunk):
+    """Reference loop condition (run until the time grid is full) with trajectories that end
+    in different launches; single carrier and multi-carrier; state carried across launches."""
+    for species in ([1, 0], [5, 0]):
+        ex = H.load_example('hematite', species_count=species)
+        run = H.run_parameters(ex)
+        n_traj = 12
+        occ = K.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed=33)
+        kw = dict(dt_grid=run.time_interval / 4, n_path=300, stop_at_grid_end=True)
+        system = K.KmcSystem(ctx, run, ex.P)
+        ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=33, refresh_interval=refresh, **kw)
+        launches = 0
+        while ens.advance_resident(chunk) > 0:
+            launches += 1
+        got = ens.read()
+        ens.close()
+        system.close()
+        ref = O.KmcOracle(run, ex.P, rng_mode=1, seed=33, **kw).ensemble(occ)
+        assert launches >= 2
+        assert len(set(ref['n_steps'])) > 1
+        assert np.array_equal(got['n_steps'], ref['n_steps'])
+        assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+        assert np.all(got['time'] >= 299 * kw['dt_grid'])
+
+
+def test_bad_arguments_are_rejected(ctx):
+    ex = H.load_example('hematite', species_count=[2, 0])
+    run = H.run_parameters(ex)
+    system = K.KmcSystem(ctx, run, ex.P)
+    occ = K.philox_initial_occupancy(run.tables, 2, 2, seed=1)
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, refresh_interval=16, step_limit=64,
+                        stop_at_grid_end=False)
+    with pytest.raises(nat.NativeError, match='multiple of refresh_interval'):
+        ens.advance_resident(24)
+    ens.close()
+    with pytest.raises(nat.NativeError, match='never end'):
+        K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, stop_at_grid_end=False, step_limit=0)
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_REPLAY)
+    with pytest.raises(nat.NativeError, match='REPLAY'):
+        ens.advance_resident(8)
+    ens.close()
+    with pytest.raises(ValueError):
+        K.KmcSystem(ctx, run, ex.P[:5])
+    system.close()
+
+
 def test_sharding_is_invisible(ctx):
     """Trajectories keyed by global id: running [0,32) and [32,64) separately equals [0,64)."""
     ex, run = _philox_case(species=(4, 0))
