@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 
 namespace pycd {
@@ -203,6 +204,140 @@ ewald_fourier_kernel(const double *__restrict__ theta, long long n_sites, long l
     }
 }
 
+// mma.sync.m8n8k4.f64: the fp64 tensor-core path of sm_100 (tcgen05 has no fp64 kind); 256
+// FMAs per warp instruction.  Panels are stored as [k/4][site][4] so that the A (row) and
+// B (col) fragments of a k4 slice are one conflict-free LDS.64 per lane (lane l reads element
+// [site0 + l/4][k0 + l%4] = base + l).
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------
+// Phased DMMA kernel (the default): all 8 warps generate the panels of a chunk, then all 8
+// accumulate with mma.sync.m8n8k4.f64; two CTAs share an SM so that one CTA's generation
+// phase runs under the other's DMMA stream.  (Dedicated producer warps starve: their
+// dependent DFMA chains queue behind 16-cycle DMMA issues on the shared FP64 pipe.)
+// Measured register-only ceilings on this B200 (tools/fp64_peak.cu): DMMA 37.1 TFLOP/s,
+// register-tiled DFMA 25-28 TFLOP/s.
+template <int BM, int BN, int WM, int WN, int KC>
+__global__ void __launch_bounds__(EW_THREADS, 2)
+ewald_fourier_dmma_kernel(const double *__restrict__ theta, long long n_sites, long long row0,
+                          long long n_rows, const KEntry *__restrict__ kent,
+                          const double *__restrict__ kw, int n_chunks, int k_split, int n_row_tiles,
+                          int n_col_tiles, double *__restrict__ out)
+{
+    static_assert((BM / WM) * (BN / WN) == EW_THREADS / 32, "8 warps must tile the CTA tile");
+    static_assert(WM % 8 == 0 && WN % 8 == 0 && KC % 2 == 0, "m8n8k4 fragments");
+    constexpr int NS = BM + BN;
+    constexpr bool SPLIT_ROWS = (NS > EW_THREADS);        // skinny tile: BN == 256 columns + BM rows
+    static_assert(!SPLIT_ROWS || BN == EW_THREADS, "skinny tile: one column site per thread");
+    constexpr int ROW_PIECES = SPLIT_ROWS ? EW_THREADS / BM : 1;
+    constexpr int PIECE = KC / ROW_PIECES;
+    static_assert(!SPLIT_ROWS || (KC % ROW_PIECES == 0 && PIECE >= 1), "row pieces must tile the chunk");
+    constexpr int MT = WM / 8, NT = WN / 8, KG = KC / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);    // [KG][BM][4]  rows, weighted
+    double *Bs = As + 2 * KC * BM;                         // [KG][BN][4]  columns
+    double *s_w = Bs + 2 * KC * BN;                        // [KC]
+    KEntry *s_ent = reinterpret_cast<KEntry *>(s_w + KC);  // [KC]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int bid = blockIdx.x;
+    const int ct = bid % n_col_tiles; bid /= n_col_tiles;
+    const int rt = bid % n_row_tiles; bid /= n_row_tiles;
+    const int ks = bid;
+    const int c0 = (int)(((long long)ks * n_chunks) / k_split);
+    const int c1 = (int)(((long long)(ks + 1) * n_chunks) / k_split);
+
+    auto row_site = [&](int r) -> long long {
+        const long long s = row0 + (long long)rt * BM + r;
+        return s < n_sites ? s : n_sites - 1;
+    };
+    auto col_site = [&](int c) -> long long {
+        const long long s = (long long)ct * BN + c;
+        return s < n_sites ? s : n_sites - 1;
+    };
+    // primary walker: dense tile -> tile site tid (rows first, then columns; threads >= NS
+    // idle during generation); skinny -> column tid
+    const bool prim_active = SPLIT_ROWS || tid < NS;
+    const bool prim_is_row = !SPLIT_ROWS && tid < BM;
+    const int prim_idx = SPLIT_ROWS ? tid : (prim_is_row ? tid : tid - BM);
+    PhaseWalker pw, rw;
+    pw.init(theta, prim_is_row ? row_site(prim_idx) : col_site(prim_active ? prim_idx : 0));
+    const int r_site = tid % BM, r_piece = tid / BM;
+    if (SPLIT_ROWS) rw.init(theta, row_site(r_site));
+
+    const int m0 = (wid % (BM / WM)) * WM, n0 = (wid / (BM / WM)) * WN;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int chunk = c0; chunk < c1; ++chunk) {
+        __syncthreads();  // previous product finished with the panels
+        if (tid < KC) {
+            s_ent[tid] = kent[(long long)chunk * KC + tid];
+            s_w[tid] = kw[(long long)chunk * KC + tid];
+        }
+        __syncthreads();
+        if (prim_active) {
+#pragma unroll 4
+            for (int e = 0; e < KC; ++e) {
+                pw.step(s_ent[e], chunk == c0 && e == 0);
+                if (prim_is_row) {
+                    const double w = s_w[e];
+                    *reinterpret_cast<double2 *>(&As[((e >> 1) * BM + prim_idx) * 4 + (e & 1) * 2]) =
+                        make_double2(w * pw.c, w * pw.s);
+                } else {
+                    *reinterpret_cast<double2 *>(&Bs[((e >> 1) * BN + prim_idx) * 4 + (e & 1) * 2]) =
+                        make_double2(pw.c, pw.s);
+                }
+            }
+        }
+        if (SPLIT_ROWS) {
+#pragma unroll
+            for (int q = 0; q < PIECE; ++q) {
+                const int e = r_piece * PIECE + q;
+                rw.step(s_ent[e], q == 0);
+                const double w = s_w[e];
+                *reinterpret_cast<double2 *>(&As[((e >> 1) * BM + r_site) * 4 + (e & 1) * 2]) =
+                    make_double2(w * rw.c, w * rw.s);
+            }
+        }
+        __syncthreads();
+        const double *Aw = As + (size_t)m0 * 4 + lane;
+        const double *Bw = Bs + (size_t)n0 * 4 + lane;
+#pragma unroll
+        for (int g = 0; g < KG; ++g) {
+            double a[MT], b[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) a[i] = Aw[(g * BM + i * 8) * 4];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) b[j] = Bw[(g * BN + j * 8) * 4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+
+    double *o = out + (long long)ks * n_rows * n_sites;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const long long row = (long long)rt * BM + m0 + i * 8 + (lane >> 2);
+        if (row >= n_rows) continue;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const long long col = (long long)ct * BN + n0 + j * 8 + (lane & 3) * 2;
+            if (col < n_sites) o[row * n_sites + col] = acc[i][j][0];
+            if (col + 1 < n_sites) o[row * n_sites + col + 1] = acc[i][j][1];
+        }
+    }
+}
+
 struct FinishParams {
     double cell[9], cellinv[9];
     int pbc[3];
@@ -341,6 +476,21 @@ static void launch_fourier(pycd_ctx *ctx, const double *theta, long long n, long
     check_launch(ctx, "ewald_fourier_kernel");
 }
 
+template <int BM, int BN, int WM, int WN, int KC>
+static void launch_fourier_dmma(pycd_ctx *ctx, const double *theta, long long n, long long row0,
+                                long long n_rows, const KEntry *kent, const double *kw, int n_chunks,
+                                int k_split, double *out) {
+    auto kern = ewald_fourier_dmma_kernel<BM, BN, WM, WN, KC>;
+    const size_t smem = sizeof(double) * (size_t)(2 * KC) * (BM + BN) + (sizeof(KEntry) + sizeof(double)) * KC;
+    PYCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_row_tiles = (int)((n_rows + BM - 1) / BM), n_col_tiles = (int)((n + BN - 1) / BN);
+    const long long grid = (long long)k_split * n_row_tiles * n_col_tiles;
+    PYCD_REQUIRE(grid < (1ll << 31), "grid too large");
+    kern<<<(unsigned)grid, EW_THREADS, smem, ctx->stream>>>(
+        theta, n, row0, n_rows, kent, kw, n_chunks, k_split, n_row_tiles, n_col_tiles, out);
+    check_launch(ctx, "ewald_fourier_dmma_kernel");
+}
+
 }  // namespace pycd
 
 using namespace pycd;
@@ -357,7 +507,11 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         // wide tile (128x128, 32-entry chunks, 1 CTA/SM) for big row blocks, skinny tile
         // (32x256, 16-entry chunks, 2 CTAs/SM) for the rows of one unit cell
         const bool wide = n_rows > 64;
-        const int KC = wide ? 32 : 16;
+        // kernel variant: "dmma" (default: DMMA accumulation, 2 CTAs/SM) or "dfma" (register-tiled
+        // DFMA; kept for A/B measurements, PYCD_EWALD_VARIANT=dfma)
+        const char *var_env = getenv("PYCD_EWALD_VARIANT");
+        const bool use_dmma = !(var_env && std::string(var_env) == "dfma");
+        const int KC = (wide && !use_dmma) ? 32 : 16;
 
         std::vector<KEntry> ent;
         std::vector<double> w;
@@ -384,13 +538,13 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
                                       cudaMemcpyHostToDevice, ctx->stream));
             PYCD_CUDA(cudaMemcpyAsync(kw.p, w.data(), w.size() * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
-            const long long bm = wide ? 128 : 32, bn = wide ? 128 : 256;
+            const long long bm = wide ? (use_dmma ? 64 : 128) : 32, bn = wide ? 128 : 256;
             const long long tiles = ((n_rows + bm - 1) / bm) * ((n + bn - 1) / bn);
             // split-k so that the grid fills whole waves of the SMs (1 CTA/SM): among the
             // candidates pick the best-filled last wave, preferring fewer splits on ties
             const long long ws_cap = std::max(1ll, (1ll << 30) / (n_rows * n * 8));
             const long long ks_max = std::min({(long long)n_chunks, ws_cap, 32ll});
-            const long long slots = (long long)ctx->n_sm * (wide ? 1 : 2);
+            const long long slots = (long long)ctx->n_sm * ((use_dmma || !wide) ? 2 : 1);
             double best_fill = -1.0;
             for (long long ks = 1; ks <= ks_max; ++ks) {
                 const long long grid = tiles * ks;
@@ -407,7 +561,13 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         }
         KernelTimer tf(ctx, KC_EWALD_FOURIER);
         if (n_chunks > 0) {
-            if (wide)
+            if (use_dmma && wide)
+                launch_fourier_dmma<64, 128, 32, 32, 16>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                         n_chunks, k_split, partials);
+            else if (use_dmma)
+                launch_fourier_dmma<32, 256, 32, 32, 16>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                         n_chunks, k_split, partials);
+            else if (wide)
                 launch_fourier<128, 128, 8, 8, 32, 1>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
                                                      n_chunks, k_split, partials);
             else
