@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 namespace pycd {
 
@@ -680,6 +681,407 @@ kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Carrier-per-thread variant: thread c owns carrier c and its NN processes (block = CT
+// threads, CT = number of carriers, a multiple of 32).  The per-process state lives in
+// registers, the old-site elements P[a, .] are shared by the NN slots of a carrier, the scan is
+// one local prefix + one warp scan, and a step needs 3 block barriers.  Same arithmetic as
+// kmc_step_kernel (stateless order for R = 1, incremental patches otherwise); ~3x fewer warp
+// instructions per KMC step at (CT, NN) = (64, 4).
+template <int CT, int NN, bool COMPACT>
+__global__ void __launch_bounds__(CT)
+kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
+{
+    constexpr int NW = CT / 32;
+    constexpr int NP = CT * NN;
+    static_assert(CT % 32 == 0 && CT >= 32, "one warp-aligned thread per carrier");
+    const int traj = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+
+    __shared__ double s_k[NP], s_cum[NP];          // rates and running sums of this step
+    __shared__ int s_b[NP], s_be[NP];              // new site / its centre index per process
+    __shared__ unsigned s_bp[NP];
+    __shared__ int s_occ[CT], s_occe[CT];
+    __shared__ unsigned s_occp[CT];
+    __shared__ double s_disp[3 * CT], s_row[3 * CT], s_drift[3 * CT];
+    __shared__ double s_red[NN][NW > 1 ? NW : 1];
+    __shared__ double s_wsum[NW > 1 ? NW : 1];
+    __shared__ double s_u[4];
+    __shared__ StepCtl s_ctl[2];
+    __shared__ int s_wfirst[NW > 1 ? NW : 1];
+    __shared__ int s_sel[2];
+    __shared__ double s_g0[NP];                    // delta-G0 per process (energy outputs only)
+
+    if (E.done[traj]) {
+        if (tid == 0 && A.steps_done) A.steps_done[traj] = 0;
+        return;
+    }
+    const double kT = E.kT_traj ? E.kT_traj[traj] : S.kT;
+    double fld[3] = {S.field[0], S.field[1], S.field[2]};
+    int field_active = S.field_active;
+    if (E.field_traj) {
+        fld[0] = E.field_traj[3 * traj];
+        fld[1] = E.field_traj[3 * traj + 1];
+        fld[2] = E.field_traj[3 * traj + 2];
+        field_active = (fld[0] != 0.0 || fld[1] != 0.0 || fld[2] != 0.0);
+    }
+    const double two_qc = __dmul_rn(2.0, S.qc);
+    const long long steps_total = E.n_steps[traj];
+    const unsigned long long traj_gid = E.traj_id0 + (unsigned long long)traj;
+    const int R = E.refresh_interval;
+    const int rng_tid = (CT > 32) ? 32 : 0;
+    const bool want_energy = (E.energy != nullptr);
+
+    auto draw = [&](long long step_local, double *dst) {  // u1 and -log(u2) of a step
+        double u1, u2;
+        if (E.rng_mode == PYCD_RNG_REPLAY) {
+            if (step_local < A.max_steps) {
+                const double *dr = A.draws + ((long long)traj * A.max_steps + step_local) * 2;
+                u1 = dr[0];
+                u2 = dr[1];
+            } else {
+                u1 = 0.0; u2 = 1.0;
+            }
+        } else {
+            philox_uniforms(E.seed, traj_gid, (unsigned long long)(steps_total + step_local), u1, u2);
+        }
+        dst[0] = u1;
+        dst[1] = -log(u2);
+    };
+
+    // ---- per-thread (per-carrier) state in registers ----
+    Site a;            // current site of this carrier
+    int ae;            // its centre index
+    Site b[NN];
+    int be[NN];
+    double t01[NN], t02[NN], shift[NN], lam[NN], vab[NN], fs[NN];
+
+    auto load_static = [&](Site na, int ne) {   // everything of the NN processes but the carrier sums
+        a = na; ae = ne;
+#pragma unroll
+        for (int s = 0; s < NN; ++s) {
+            const ProcStatic ps = load_process_static<COMPACT>(S, NN, s, na, ne, fld, field_active);
+            b[s] = ps.b; be[s] = ps.be;
+            t02[s] = ps.t02; shift[s] = ps.shift; lam[s] = ps.lam; vab[s] = ps.vab; fs[s] = ps.fs;
+            t01[s] = ps.vl;
+        }
+    };
+    auto publish = [&]() {                      // make the new sites of my processes visible
+#pragma unroll
+        for (int s = 0; s < NN; ++s) {
+            s_b[tid * NN + s] = b[s].idx;
+            s_bp[tid * NN + s] = b[s].pack;
+            s_be[tid * NN + s] = be[s];
+        }
+    };
+
+    {
+        const int s0 = E.occ[(long long)traj * CT + tid];
+        s_occ[tid] = s0;
+        s_occe[tid] = S.site_centre[s0];
+        s_occp[tid] = COMPACT ? S.site_pack[s0] : 0u;
+    }
+    for (int d = tid; d < 3 * CT; d += CT) {
+        s_disp[d] = E.disp[(long long)traj * 3 * CT + d];
+        s_row[d] = E.row[(long long)traj * 3 * CT + d];
+        s_drift[d] = E.drift[(long long)traj * 3 * CT + d];
+    }
+    double t = E.t[traj];
+    double energy = (E.energy && tid == 0) ? E.energy[traj] : 0.0;
+    long long start = E.start_idx[traj];
+    long long n_tie = 0, n_clamp = 0;
+    long long step_local = 0;
+    int finished = 0;
+    int to_refresh = (R <= 1) ? 0 : (int)((R - (steps_total % R)) % R);
+    if (tid == 0) {
+        s_ctl[0].r0 = s_ctl[0].r1 = 0; s_ctl[0].fin = 0;
+        s_ctl[1].r0 = s_ctl[1].r1 = 0; s_ctl[1].fin = 0;
+    }
+    if (tid == rng_tid) draw(0, s_u);
+    __syncthreads();
+    {
+        Site na;
+        na.idx = s_occ[tid];
+        na.pack = s_occp[tid];
+        load_static(na, s_occe[tid]);
+        publish();
+    }
+    bool need_full = true;   // the cached sums are rebuilt at the first step of every launch
+    __syncthreads();
+
+    while (true) {
+        const int par = (int)(step_local & 1);
+        {
+            const StepCtl ctl = s_ctl[par ^ 1];
+            if (ctl.r1 > ctl.r0) {  // unwrapped[start:end] = unwrapped[start-1] + displacement, core.py:2852-2854
+                for (int d = tid; d < 3 * CT; d += CT) {
+                    const double v = s_row[d] + s_disp[d];
+                    s_row[d] = v;
+                    s_disp[d] = 0.0;
+                    if (E.unwrapped) {
+                        double *dst = E.unwrapped + ((long long)traj * E.n_path + ctl.r0) * 3 * CT + d;
+                        for (long long r = ctl.r0; r < ctl.r1; ++r, dst += 3 * CT) *dst = v;
+                    }
+                }
+            }
+            finished = ctl.fin;
+        }
+        if (finished || step_local >= A.max_steps) break;
+
+        // ---- full re-gather (every R steps; every step for R = 1): carriers in order ----
+        const bool full = need_full || (to_refresh == 0);
+        need_full = false;
+        to_refresh = (R <= 1) ? 0 : ((to_refresh == 0) ? R - 1 : to_refresh - 1);
+        if (full) {
+            const USite ua = unpack<COMPACT>(a);
+            USite ub[NN];
+#pragma unroll
+            for (int s = 0; s < NN; ++s) {
+                ub[s] = unpack<COMPACT>(b[s]);
+                t01[s] = __dsub_rn(ld_vlat<COMPACT>(S, b[s]), ld_vlat<COMPACT>(S, a));
+            }
+            constexpr int GB = 2;
+            for (int c0 = 0; c0 < CT; c0 += GB) {
+                double pa[GB], pb[GB][NN];
+#pragma unroll
+                for (int j = 0; j < GB; ++j) {
+                    Site sc;
+                    sc.idx = s_occ[c0 + j];
+                    sc.pack = s_occp[c0 + j];
+                    const USite usc = unpack<COMPACT>(sc);
+                    pa[j] = ld_pair<COMPACT>(S, ua, usc);
+#pragma unroll
+                    for (int s = 0; s < NN; ++s) pb[j][s] = ld_pair<COMPACT>(S, ub[s], usc);
+                }
+#pragma unroll
+                for (int j = 0; j < GB; ++j)
+#pragma unroll
+                    for (int s = 0; s < NN; ++s)
+                        t01[s] = __dadd_rn(t01[s], __dmul_rn(S.qc, __dsub_rn(pb[j][s], pa[j])));
+            }
+        }
+
+        // ---- rates, local prefix ----
+        double k[NN], loc[NN];
+        double run = 0.0;
+#pragma unroll
+        for (int s = 0; s < NN; ++s) {
+            const double ew = __dmul_rn(two_qc, __dadd_rn(t01[s], t02[s]));              // core.py:2016
+            const double g0 = __dadd_rn(ew, shift[s]);
+            const double lg = __dadd_rn(lam[s], g0);
+            const double gs = __dsub_rn(__dsub_rn(__ddiv_rn(__dmul_rn(lg, lg), __dmul_rn(4.0, lam[s])), vab[s]),
+                                        fs[s]);                                            // core.py:2045
+            k[s] = __dmul_rn(S.vn, pow_np_e(__ddiv_rn(-gs, kT)));                           // core.py:2047
+            run += k[s];
+            loc[s] = run;
+            s_k[tid * NN + s] = k[s];
+            if (want_energy) s_g0[tid * NN + s] = g0;
+        }
+        // ---- warp scan of the per-thread totals, cross-warp prefix ----
+        double x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        double pre = x - run, ktot;   // exclusive prefix inside the warp
+        if (NW > 1) {
+            if (lane == 31) s_wsum[wid] = x;
+            __syncthreads();  // (A)
+            double before = 0.0, tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const double v = s_wsum[w];
+                if (w < wid) before += v;
+                tot += v;
+            }
+            pre += before;
+            ktot = tot;
+        } else {
+            ktot = __shfl_sync(0xffffffffu, x, 31);
+        }
+        const double u1 = s_u[2 * par], nlog_u2 = s_u[2 * par + 1];
+        const double thresh = u1 * ktot, tie_w = TIE_TOL * ktot;
+        int first_local = NN;
+#pragma unroll
+        for (int s = NN - 1; s >= 0; --s) {
+            const double cum = pre + loc[s];
+            s_cum[tid * NN + s] = cum;
+            if (cum > thresh) first_local = s;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, first_local < NN);
+        int first = INT_MAX;
+        if (m) {
+            const int src = __ffs(m) - 1;
+            first = (wid * 32 + src) * NN + __shfl_sync(0xffffffffu, first_local, src);
+        }
+        if (NW > 1) {
+            if (lane == 0) s_wfirst[wid] = first;
+        }
+        __syncthreads();  // (B) s_k, s_cum, s_wfirst visible
+        int sel = first;
+        if (NW > 1) {
+            sel = INT_MAX;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sel = min(sel, s_wfirst[w]);
+        }
+        bool tie = (sel == INT_MAX);
+        if (!tie) {
+            const double hi = s_cum[sel], lo = sel > 0 ? s_cum[sel - 1] : 0.0;
+            tie = (hi - thresh < tie_w) || (sel > 0 && thresh - lo < tie_w);
+        }
+        if (tie) {  // block-uniform: redo the selection in the reference's sequential order
+            if (tid == 0) {
+                double kseq = 0.0;
+                for (int p = 0; p < NP; ++p) kseq += s_k[p];
+                double cum = 0.0;
+                int s2 = -1;
+                for (int p = 0; p < NP; ++p) {
+                    cum += s_k[p] / kseq;
+                    if (cum > u1) { s2 = p; break; }
+                }
+                if (s2 < 0) { s2 = NP - 1; ++n_clamp; }
+                ++n_tie;
+                s_sel[0] = s2;
+            }
+            __syncthreads();
+            sel = s_sel[0];
+        }
+
+        const int cs = sel / NN, slot = sel - cs * NN;
+        Site a_old, b_new;
+        a_old.idx = s_occ[cs];
+        a_old.pack = s_occp[cs];
+        b_new.idx = s_b[sel];
+        b_new.pack = s_bp[sel];
+        const int e_old = s_occe[cs], e_new = s_be[sel];
+        const USite u_old = unpack<COMPACT>(a_old), u_new = unpack<COMPACT>(b_new);
+        const bool next_full = (to_refresh == 0);
+
+        // ---- long-latency loads of the tail, issued before the barrier ----
+        double hv0 = 0.0, hv1 = 0.0, hv2 = 0.0;
+        if (tid == 0) {
+            const double *hv = S.hopvec + ((long long)e_old * NN + slot) * 3;
+            hv0 = __ldg(hv); hv1 = __ldg(hv + 1); hv2 = __ldg(hv + 2);
+        }
+        double patch[NN];
+        if (!next_full) {
+            if (tid != cs) {
+                // untouched carrier: q_c [(P[b_s,b] - P[a,b]) - (P[b_s,a_old] - P[a,a_old])] per slot
+                const USite ua = unpack<COMPACT>(a);
+                const double pa_new = ld_pair<COMPACT>(S, ua, u_new), pa_old = ld_pair<COMPACT>(S, ua, u_old);
+#pragma unroll
+                for (int s = 0; s < NN; ++s) {
+                    const USite ub = unpack<COMPACT>(b[s]);
+                    const double pb_new = ld_pair<COMPACT>(S, ub, u_new), pb_old = ld_pair<COMPACT>(S, ub, u_old);
+                    patch[s] = S.qc * (pb_new - pa_new) - S.qc * (pb_old - pa_old);
+                }
+            } else {
+                load_static(b_new, e_new);   // my carrier moved: new processes (t01 = V_lat part for now)
+            }
+            // contribution of MY carrier's site to the moved carrier's new processes
+            Site sc = (tid == cs) ? b_new : Site{s_occ[tid], s_occp[tid]};
+            const USite usc = unpack<COMPACT>(sc);
+            const double p_base = ld_pair<COMPACT>(S, u_new, usc);
+            double term[NN];
+#pragma unroll
+            for (int s = 0; s < NN; ++s) {
+                Site nbr;
+                nbr.idx = __ldg(S.neigh + (long long)e_new * NN + s);
+                nbr.pack = COMPACT ? __ldg(S.neigh_pack + (long long)e_new * NN + s) : 0u;
+                term[s] = S.qc * (ld_pair<COMPACT>(S, unpack<COMPACT>(nbr), usc) - p_base);
+            }
+#pragma unroll
+            for (int s = 0; s < NN; ++s) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) term[s] += __shfl_xor_sync(0xffffffffu, term[s], o);
+                if (lane == 0) s_red[s][wid] = term[s];
+            }
+        }
+
+        // ---- thread 0: time advance, grid bookkeeping, hop, core.py:2802-2830, 2844-2861 ----
+        if (tid == 0) {
+            t += nlog_u2 / ktot;
+            const long long end = (long long)(t / E.dt_grid);
+            const long long start_before = start;
+            StepCtl ctl;
+            ctl.r0 = 0; ctl.r1 = 0; ctl.fin = 0; ctl.pad = 0;
+            if (end >= start + 1) {
+                const long long e2 = end >= E.n_path ? E.n_path : end;
+                if (start < E.n_path) { ctl.r0 = start; ctl.r1 = e2; }
+                start = e2;
+            }
+            if (E.energy) {  // output_data energy / delg_0, core.py:2807-2809, 2826, 2855-2857
+                const double g0 = s_g0[sel];
+                const long long hi_r = end < E.n_path ? end : E.n_path;
+                for (long long r = start_before; r < hi_r; ++r) E.dg0_grid[(long long)traj * E.n_path + r] = g0;
+                energy += g0;
+                for (long long r = ctl.r0; r < ctl.r1; ++r) E.energy_grid[(long long)traj * E.n_path + r] = energy;
+            }
+            if (E.stop_at_grid_end && end >= E.n_path) ctl.fin = 1;
+            if (E.step_limit > 0 && steps_total + step_local + 1 >= E.step_limit) ctl.fin = 1;
+            s_ctl[par] = ctl;
+            const double kp = s_k[sel];
+            s_disp[3 * cs] += hv0; s_disp[3 * cs + 1] += hv1; s_disp[3 * cs + 2] += hv2;
+            if (field_active) {
+                s_drift[3 * cs] += hv0 * kp; s_drift[3 * cs + 1] += hv1 * kp; s_drift[3 * cs + 2] += hv2 * kp;
+            }
+            if (A.events_out) A.events_out[(long long)traj * A.max_steps + step_local] = sel;
+            if (A.times_out) A.times_out[(long long)traj * A.max_steps + step_local] = t;
+        }
+        if (tid == rng_tid) draw(step_local + 1, s_u + 2 * (par ^ 1));
+        __syncthreads();  // (C) s_red, s_ctl, s_disp visible; all reads of s_occ[cs] / s_b[sel] done
+
+        if (tid == cs) {
+            s_occ[cs] = b_new.idx;
+            s_occe[cs] = e_new;
+            s_occp[cs] = b_new.pack;
+            if (next_full) load_static(b_new, e_new);
+            publish();
+        }
+        if (!next_full) {
+            if (tid != cs) {
+#pragma unroll
+                for (int s = 0; s < NN; ++s) t01[s] += patch[s];
+            } else {
+#pragma unroll
+                for (int s = 0; s < NN; ++s) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) acc += s_red[s][w];
+                    t01[s] += acc;
+                }
+            }
+        }
+        ++step_local;
+        // s_occ / s_b of the moved carrier are read by the others only after barriers (A)/(B) of the
+        // next step -- except by a full re-gather, which starts right away
+        if (next_full) __syncthreads();
+    }
+
+    // ---- write the state back ----
+    __syncthreads();
+    E.occ[(long long)traj * CT + tid] = s_occ[tid];
+    for (int d = tid; d < 3 * CT; d += CT) {
+        E.disp[(long long)traj * 3 * CT + d] = s_disp[d];
+        E.row[(long long)traj * 3 * CT + d] = s_row[d];
+        E.drift[(long long)traj * 3 * CT + d] = s_drift[d];
+    }
+    if (step_local > 0)
+        for (int p = tid; p < NP; p += CT) E.rates[(long long)traj * NP + p] = s_k[p];
+    if (tid == 0) {
+        E.t[traj] = t;
+        if (E.energy) E.energy[traj] = energy;
+        E.start_idx[traj] = start;
+        E.n_steps[traj] = steps_total + step_local;
+        E.near_tie[traj] += n_tie;
+        E.clamped[traj] += n_clamp;
+        if (finished) E.done[traj] = 1;
+        if (A.steps_done) A.steps_done[traj] = step_local;
+    }
+}
+
 // V_lat = P . q_lat, one warp per row, double-double accumulation so that the
 // differences V_lat[b]-V_lat[a] keep ~1e-16 Ha accuracy at N = 30 000.
 __global__ void __launch_bounds__(256)
@@ -1043,10 +1445,24 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         PYCD_REQUIRE(smem <= 200 * 1024, "trajectory state does not fit in shared memory");
         const bool cp = ens->sys->compact;
         KernelTimer tk(ctx, KC_KMC_STEP);
-        if (E.n_proc <= 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
+        // PYCD_KMC_VARIANT=process keeps the one-thread-per-process kernel for A/B measurements
+        const char *kv = getenv("PYCD_KMC_VARIANT");
+        const bool per_process = kv && std::string(kv) == "process";
+        int bs_force = 0;   // diagnostic: PYCD_KMC_BS forces the block size of the generic kernel
+        if (const char *e = getenv("PYCD_KMC_BS")) bs_force = atoi(e);
+        if (bs_force == 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (bs_force == 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (bs_force == 128) launch_step<128>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (bs_force == 256) launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
+        else if (E.n_proc <= 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (E.n_proc <= 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (E.n_proc <= 128) launch_step<128>(ctx, cp, ens->sys->dev, E, A, smem);
-        else if (E.C == 64 && ens->sys->dev.nn == 4 && cp)   // the benchmark shape: fully specialised
+        else if (E.C == 64 && ens->sys->dev.nn == 4 && !per_process) {
+            // the benchmark shape: one thread per carrier, process state in registers
+            if (cp) kmc_step_carrier_kernel<64, 4, true><<<(unsigned)E.n_traj, 64, 0, ctx->stream>>>(ens->sys->dev, E, A);
+            else kmc_step_carrier_kernel<64, 4, false><<<(unsigned)E.n_traj, 64, 0, ctx->stream>>>(ens->sys->dev, E, A);
+            check_launch(ctx, "kmc_step_carrier_kernel");
+        } else if (E.C == 64 && ens->sys->dev.nn == 4 && cp)   // one thread per process, fully specialised
             launch_step_impl<256, true, 64, 4>(ctx, ens->sys->dev, E, A, smem);
         else launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
         tk.stop(1);

@@ -257,6 +257,80 @@ def test_bad_arguments_are_rejected(ctx):
     system.close()
 
 
+@pytest.fixture(scope='module')
+def hematite_64e(ctx):
+    """Hematite 3x3x2 (N = 540, 216 Fe), 64 electrons: the (carriers, slots) = (64, 4) shape
+    served by the carrier-per-thread kernel.  Ewald array computed on the GPU."""
+    from pycd_b200.kmc import RunParameters
+    from pycd_b200.lattice import Supercell
+    ex = H.load_example('hematite')
+    sim = ex.sim
+    sc = Supercell(ex.lattice, [3, 3, 2], [1, 1, 1])
+    field = {'electric': {'active': 1, 'dir': [1, 0, 0], 'ld': 0, 'mag': 1e-3}}
+    run = RunParameters(ex.lattice, sc, sc.hop_neighbor_tables(), sim['temp'], 'full', 'full',
+                        sim['t_final'], sim['time_interval'], [64, 0], {}, sim['relative_energies'], field)
+    ep = EW.EwaldParameters(sc, ex.cfg['alpha'], ex.cfg['r_cut'], ex.cfg['k_cut'])
+    p_unit, _ = EW.ewald_rows(ctx, ep, np.ascontiguousarray(sc.coordinates), 0, sc.n_per_cell)
+    dense = EW.ewald_expand(ctx, sc, p_unit, 0, sc.num_system_elements)
+    return run, p_unit, dense
+
+
+@pytest.mark.parametrize('layout', ['unit_rows', 'dense'])
+@pytest.mark.parametrize('refresh', [1, 16])
+def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
+    run, p_unit, dense = hematite_64e
+    n_traj, steps = 24, 2400
+    occ = K.philox_initial_occupancy(run.tables, n_traj, 64, seed=77)
+    kw = dict(dt_grid=run.time_interval / 4000, n_path=256, step_limit=steps, stop_at_grid_end=False)
+    system = K.KmcSystem(ctx, run, p_unit if layout == 'unit_rows' else dense, layout=layout)
+    e0 = np.linspace(-3.0, 3.0, n_traj)
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=77, refresh_interval=refresh,
+                        energy0=e0, **kw)
+    while ens.advance_resident(800) > 0:
+        pass
+    got = ens.read(rates=True)
+    eg, gg = ens.read_energy()
+    ens.close()
+    system.close()
+    orc = O.KmcOracle(run, dense, rng_mode=1, seed=77, **kw)
+    ref = orc.ensemble(occ)
+    assert np.array_equal(got['n_steps'], ref['n_steps'])
+    assert np.array_equal(got['occupancy'], ref['occupancy'])
+    assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+    assert np.allclose(got['drift'], ref['drift'], rtol=1e-9, atol=1e-300)
+    one = orc.trajectory(occ[3], traj_id=3, energy0=e0[3])
+    assert np.allclose(eg[3], one['energy_grid'], rtol=1e-11, atol=1e-13)
+    assert np.allclose(gg[3], one['dg0_grid'], rtol=1e-9, atol=1e-15)
+
+
+def test_64_carriers_replay_and_first_step_rates(ctx, hematite_64e):
+    import random
+    run, p_unit, dense = hematite_64e
+    rngs = [random.Random(100 + i) for i in range(3)]
+    occ = np.array([run.initial_occupancy_from(r) for r in rngs])
+    system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+    probe = K.KmcEnsemble(system, occ[:1], rng_mode=nat.RNG_REPLAY)
+    probe.advance(1, draws=np.full((1, 2), 0.5))
+    rates = probe.read(unwrapped=False, rates=True)['rates'][0]
+    probe.close()
+    orc = O.KmcOracle(run, dense, n_path=40, dt_grid=run.time_interval / 2000)
+    assert np.allclose(rates, orc.trajectory(occ[0], np.full(2, 0.5))['rates0'], rtol=5e-12, atol=0)
+    # replayed MT19937 streams, reference loop condition
+    draws = [np.array([r.random() for _ in range(2 * 6000)]) for r in rngs]
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_REPLAY, n_path=40, dt_grid=run.time_interval / 2000)
+    res = ens.advance(6000, draws=np.stack(draws), want_events=True, want_times=True)
+    got = ens.read()
+    ens.close()
+    system.close()
+    for i in range(3):
+        ref = orc.trajectory(occ[i], draws[i], want_events=True, want_times=True)
+        n = ref['n_steps']
+        assert 0 < n < 6000 and int(res['steps_done'][i]) == n
+        assert np.array_equal(res['events'][i, :n], ref['events'])
+        assert np.allclose(res['times'][i, :n], ref['times'][1:], rtol=1e-12, atol=0)
+        assert np.array_equal(got['unwrapped'][i], ref['unwrapped'])
+
+
 def test_sharding_is_invisible(ctx):
     """Trajectories keyed by global id: running [0,32) and [32,64) separately equals [0,64)."""
     ex, run = _philox_case(species=(4, 0))
