@@ -26,6 +26,8 @@ struct SysDev {
     int nn;
     const int *neigh;
     const unsigned *neigh_pack; // compact only: site_pack of neigh[e][slot]
+    const int *neigh2;          // [n_centres][nn][nn]: neighbours of the neighbours (carrier kernel)
+    const unsigned *neigh2_pack;
     const double *hopvec;
     const double *lam;
     const double *vab;
@@ -702,6 +704,8 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     __shared__ double s_k[NP], s_cum[NP];          // rates and running sums of this step
     __shared__ int s_b[NP], s_be[NP];              // new site / its centre index per process
     __shared__ unsigned s_bp[NP];
+    __shared__ int s_nb[NP][NN];                   // neighbours of each process's new site (and packs):
+    __shared__ unsigned s_nbp[NP][NN];             // after a hop the next gathers need no index load
     __shared__ int s_occ[CT], s_occe[CT];
     __shared__ unsigned s_occp[CT];
     __shared__ double s_disp[3 * CT], s_row[3 * CT], s_drift[3 * CT];
@@ -755,16 +759,46 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
     int ae;            // its centre index
     Site b[NN];
     int be[NN];
-    double t01[NN], t02[NN], shift[NN], lam[NN], vab[NN], fs[NN];
+    double t01[NN], t02[NN], shift[NN], lam[NN], vab[NN], fs[NN], i4l[NN];
+    int nb2[NN][NN];
+    unsigned nb2p[NN][NN];
+    const double neg_inv_kT = -1.0 / kT;
 
-    auto load_static = [&](Site na, int ne) {   // everything of the NN processes but the carrier sums
+    // everything of the NN processes but the carrier sums.  nbr: the new sites if already known
+    // (cached neighbour list of the selected process), else they are loaded from the table.
+    auto load_static = [&](Site na, int ne, const Site *nbr) {
         a = na; ae = ne;
+        const int cls = __ldg(S.site_class + na.idx);
+        const USite ua = unpack<COMPACT>(na);
+        const double paa = ld_pair<COMPACT>(S, ua, ua), era = __ldg(S.e_rel + na.idx);
+        const double vla = ld_vlat<COMPACT>(S, na);
 #pragma unroll
         for (int s = 0; s < NN; ++s) {
-            const ProcStatic ps = load_process_static<COMPACT>(S, NN, s, na, ne, fld, field_active);
-            b[s] = ps.b; be[s] = ps.be;
-            t02[s] = ps.t02; shift[s] = ps.shift; lam[s] = ps.lam; vab[s] = ps.vab; fs[s] = ps.fs;
-            t01[s] = ps.vl;
+            const long long ns = (long long)ne * NN + s;
+            if (nbr) {
+                b[s] = nbr[s];
+            } else {
+                b[s].idx = __ldg(S.neigh + ns);
+                b[s].pack = COMPACT ? __ldg(S.neigh_pack + ns) : 0u;
+            }
+            be[s] = __ldg(S.site_centre + b[s].idx);
+            t02[s] = __dmul_rn(S.qc, __dsub_rn(paa, ld_pair<COMPACT>(S, ua, unpack<COMPACT>(b[s]))));
+            shift[s] = __dsub_rn(__ldg(S.e_rel + b[s].idx), era);
+            lam[s] = __ldg(S.lam + cls * NN + s);
+            vab[s] = __ldg(S.vab + cls * NN + s);
+            i4l[s] = 1.0 / (4.0 * lam[s]);
+            fs[s] = 0.0;
+            if (field_active) {
+                const double *hv = S.hopvec + ns * 3;
+                fs[s] = __dmul_rn(0.5, __dadd_rn(__dadd_rn(__dmul_rn(fld[0], hv[0]), __dmul_rn(fld[1], hv[1])),
+                                                 __dmul_rn(fld[2], hv[2])));
+            }
+            t01[s] = __dsub_rn(ld_vlat<COMPACT>(S, b[s]), vla);
+#pragma unroll
+            for (int s2 = 0; s2 < NN; ++s2) {
+                nb2[s][s2] = __ldg(S.neigh2 + ns * NN + s2);
+                nb2p[s][s2] = COMPACT ? __ldg(S.neigh2_pack + ns * NN + s2) : 0u;
+            }
         }
     };
     auto publish = [&]() {                      // make the new sites of my processes visible
@@ -773,6 +807,11 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             s_b[tid * NN + s] = b[s].idx;
             s_bp[tid * NN + s] = b[s].pack;
             s_be[tid * NN + s] = be[s];
+#pragma unroll
+            for (int s2 = 0; s2 < NN; ++s2) {
+                s_nb[tid * NN + s][s2] = nb2[s][s2];
+                s_nbp[tid * NN + s][s2] = nb2p[s][s2];
+            }
         }
     };
 
@@ -804,7 +843,7 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         Site na;
         na.idx = s_occ[tid];
         na.pack = s_occp[tid];
-        load_static(na, s_occe[tid]);
+        load_static(na, s_occe[tid], nullptr);
         publish();
     }
     bool need_full = true;   // the cached sums are rebuilt at the first step of every launch
@@ -841,7 +880,7 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                 ub[s] = unpack<COMPACT>(b[s]);
                 t01[s] = __dsub_rn(ld_vlat<COMPACT>(S, b[s]), ld_vlat<COMPACT>(S, a));
             }
-            constexpr int GB = 2;
+            constexpr int GB = 8;
             for (int c0 = 0; c0 < CT; c0 += GB) {
                 double pa[GB], pb[GB][NN];
 #pragma unroll
@@ -870,9 +909,14 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             const double ew = __dmul_rn(two_qc, __dadd_rn(t01[s], t02[s]));              // core.py:2016
             const double g0 = __dadd_rn(ew, shift[s]);
             const double lg = __dadd_rn(lam[s], g0);
-            const double gs = __dsub_rn(__dsub_rn(__ddiv_rn(__dmul_rn(lg, lg), __dmul_rn(4.0, lam[s])), vab[s]),
-                                        fs[s]);                                            // core.py:2045
-            k[s] = __dmul_rn(S.vn, pow_np_e(__ddiv_rn(-gs, kT)));                           // core.py:2047
+            if (R <= 1) {   // stateless mode: the reference's operation order, divisions included
+                const double gs = __dsub_rn(__dsub_rn(__ddiv_rn(__dmul_rn(lg, lg), __dmul_rn(4.0, lam[s])),
+                                                      vab[s]), fs[s]);                       // core.py:2045
+                k[s] = __dmul_rn(S.vn, pow_np_e(__ddiv_rn(-gs, kT)));                         // core.py:2047
+            } else {        // incremental mode: cached reciprocals (<= 1e-14 relative in the rate)
+                const double gs = (lg * lg) * i4l[s] - vab[s] - fs[s];
+                k[s] = S.vn * pow_np_e(gs * neg_inv_kT);
+            }
             run += k[s];
             loc[s] = run;
             s_k[tid * NN + s] = k[s];
@@ -977,8 +1021,11 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                     const double pb_new = ld_pair<COMPACT>(S, ub, u_new), pb_old = ld_pair<COMPACT>(S, ub, u_old);
                     patch[s] = S.qc * (pb_new - pa_new) - S.qc * (pb_old - pa_old);
                 }
-            } else {
-                load_static(b_new, e_new);   // my carrier moved: new processes (t01 = V_lat part for now)
+            } else {   // my carrier moved: new processes (t01 = V_lat part for now)
+                Site nbr[NN];
+#pragma unroll
+                for (int s = 0; s < NN; ++s) { nbr[s].idx = s_nb[sel][s]; nbr[s].pack = s_nbp[sel][s]; }
+                load_static(b_new, e_new, nbr);
             }
             // contribution of MY carrier's site to the moved carrier's new processes
             Site sc = (tid == cs) ? b_new : Site{s_occ[tid], s_occp[tid]};
@@ -987,9 +1034,9 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             double term[NN];
 #pragma unroll
             for (int s = 0; s < NN; ++s) {
-                Site nbr;
-                nbr.idx = __ldg(S.neigh + (long long)e_new * NN + s);
-                nbr.pack = COMPACT ? __ldg(S.neigh_pack + (long long)e_new * NN + s) : 0u;
+                Site nbr;   // new site of slot s of the moved carrier: cached with the selected process
+                nbr.idx = s_nb[sel][s];
+                nbr.pack = s_nbp[sel][s];
                 term[s] = S.qc * (ld_pair<COMPACT>(S, unpack<COMPACT>(nbr), usc) - p_base);
             }
 #pragma unroll
@@ -1037,7 +1084,7 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             s_occ[cs] = b_new.idx;
             s_occe[cs] = e_new;
             s_occp[cs] = b_new.pack;
-            if (next_full) load_static(b_new, e_new);
+            if (next_full) load_static(b_new, e_new, nullptr);
             publish();
         }
         if (!next_full) {
@@ -1128,6 +1175,20 @@ __global__ void site_pack_kernel(unsigned *out, long long n, int nb, int sy, int
     out[i] = (unsigned)b | ((unsigned)x << 8) | ((unsigned)y << 16) | ((unsigned)z << 24);
 }
 
+// neigh2[e][s][s2] = neigh[site_centre[neigh[e][s]]][s2] (+ packed form for the compact layout)
+__global__ void neigh2_kernel(const int *neigh, const int *site_centre, const unsigned *site_pack,
+                              long long n_centres, int nn, int *out, unsigned *out_pack)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_centres * nn * nn) return;
+    const int s2 = (int)(i % nn);
+    const long long es = i / nn;
+    const int mid = neigh[es];
+    const int v = neigh[(long long)site_centre[mid] * nn + s2];
+    out[i] = v;
+    out_pack[i] = site_pack ? site_pack[v] : 0u;
+}
+
 __global__ void neigh_pack_kernel(const int *neigh, const unsigned *site_pack, long long n, unsigned *out)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1147,7 +1208,8 @@ struct pycd_kmc_system {
     InBuf<int> site_centre, site_class, neigh;
     InBuf<double> hopvec, lam, vab, e_rel;
     DevBuf<double> v_lat;
-    DevBuf<unsigned> site_pack, neigh_pack;
+    DevBuf<unsigned> site_pack, neigh_pack, neigh2_pack;
+    DevBuf<int> neigh2;
     bool compact = false;
 };
 
@@ -1210,6 +1272,15 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
                                                                                   nn_tot, sys->neigh_pack.p);
                 check_launch(ctx, "neigh_pack_kernel");
             }
+            {
+                const long long n2 = (long long)d->n_centres * d->nn * d->nn;
+                sys->neigh2.alloc((size_t)n2);
+                sys->neigh2_pack.alloc((size_t)n2);
+                neigh2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(sys->neigh.p, sys->site_centre.p,
+                                                                          sys->site_pack.p, d->n_centres, d->nn,
+                                                                          sys->neigh2.p, sys->neigh2_pack.p);
+                check_launch(ctx, "neigh2_kernel");
+            }
             InBuf<double> q;
             q.bind(d->q_lat, n, s);
             // V_lat = P . q_lat: one entry per site (dense) or per basis site (compact: the
@@ -1232,6 +1303,8 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             v.field_active = d->field_active;
             v.site_pack = sys->site_pack.p;
             v.neigh_pack = sys->neigh_pack.p;
+            v.neigh2 = sys->neigh2.p;
+            v.neigh2_pack = sys->neigh2_pack.p;
             v.n_basis = d->n_basis; v.sx = d->size[0]; v.sy = d->size[1]; v.sz = d->size[2];
             sys->n_centres = d->n_centres;
             sys->n_class = d->n_class;
