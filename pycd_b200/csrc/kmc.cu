@@ -31,6 +31,7 @@ struct SysDev {
     const double *hopvec;
     const double *lam;
     const double *vab;
+    const double *i4l;        // 1/(4 lambda) per (class, slot)
     const double *e_rel;
     const double *v_lat;      // dense: [N]; compact: [n_basis]
     double qc, kT, vn;
@@ -786,7 +787,7 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
             shift[s] = __dsub_rn(__ldg(S.e_rel + b[s].idx), era);
             lam[s] = __ldg(S.lam + cls * NN + s);
             vab[s] = __ldg(S.vab + cls * NN + s);
-            i4l[s] = 1.0 / (4.0 * lam[s]);
+            i4l[s] = __ldg(S.i4l + cls * NN + s);
             fs[s] = 0.0;
             if (field_active) {
                 const double *hv = S.hopvec + ns * 3;
@@ -1011,16 +1012,32 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         }
         double patch[NN];
         if (!next_full) {
+            // (1) issue every gather first, (2) then consume: one L2 round trip for the whole tail
+            Site sc = (tid == cs) ? b_new : Site{s_occ[tid], s_occp[tid]};
+            const USite usc = unpack<COMPACT>(sc);
+            const double p_base = ld_pair<COMPACT>(S, u_new, usc);
+            double p_nbr[NN];
+#pragma unroll
+            for (int s = 0; s < NN; ++s) {
+                Site nbr;   // new site of slot s of the moved carrier: cached with the selected process
+                nbr.idx = s_nb[sel][s];
+                nbr.pack = s_nbp[sel][s];
+                p_nbr[s] = ld_pair<COMPACT>(S, unpack<COMPACT>(nbr), usc);
+            }
             if (tid != cs) {
                 // untouched carrier: q_c [(P[b_s,b] - P[a,b]) - (P[b_s,a_old] - P[a,a_old])] per slot
                 const USite ua = unpack<COMPACT>(a);
                 const double pa_new = ld_pair<COMPACT>(S, ua, u_new), pa_old = ld_pair<COMPACT>(S, ua, u_old);
+                double pb_new[NN], pb_old[NN];
 #pragma unroll
                 for (int s = 0; s < NN; ++s) {
                     const USite ub = unpack<COMPACT>(b[s]);
-                    const double pb_new = ld_pair<COMPACT>(S, ub, u_new), pb_old = ld_pair<COMPACT>(S, ub, u_old);
-                    patch[s] = S.qc * (pb_new - pa_new) - S.qc * (pb_old - pa_old);
+                    pb_new[s] = ld_pair<COMPACT>(S, ub, u_new);
+                    pb_old[s] = ld_pair<COMPACT>(S, ub, u_old);
                 }
+#pragma unroll
+                for (int s = 0; s < NN; ++s)
+                    patch[s] = S.qc * (pb_new[s] - pa_new) - S.qc * (pb_old[s] - pa_old);
             } else {   // my carrier moved: new processes (t01 = V_lat part for now)
                 Site nbr[NN];
 #pragma unroll
@@ -1028,17 +1045,9 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
                 load_static(b_new, e_new, nbr);
             }
             // contribution of MY carrier's site to the moved carrier's new processes
-            Site sc = (tid == cs) ? b_new : Site{s_occ[tid], s_occp[tid]};
-            const USite usc = unpack<COMPACT>(sc);
-            const double p_base = ld_pair<COMPACT>(S, u_new, usc);
             double term[NN];
 #pragma unroll
-            for (int s = 0; s < NN; ++s) {
-                Site nbr;   // new site of slot s of the moved carrier: cached with the selected process
-                nbr.idx = s_nb[sel][s];
-                nbr.pack = s_nbp[sel][s];
-                term[s] = S.qc * (ld_pair<COMPACT>(S, unpack<COMPACT>(nbr), usc) - p_base);
-            }
+            for (int s = 0; s < NN; ++s) term[s] = S.qc * (p_nbr[s] - p_base);
 #pragma unroll
             for (int s = 0; s < NN; ++s) {
 #pragma unroll
@@ -1189,6 +1198,12 @@ __global__ void neigh2_kernel(const int *neigh, const int *site_centre, const un
     out_pack[i] = site_pack ? site_pack[v] : 0u;
 }
 
+__global__ void inv4lambda_kernel(const double *lam, int n, double *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0 / (4.0 * lam[i]);
+}
+
 __global__ void neigh_pack_kernel(const int *neigh, const unsigned *site_pack, long long n, unsigned *out)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1207,7 +1222,7 @@ struct pycd_kmc_system {
     InBuf<double> P;
     InBuf<int> site_centre, site_class, neigh;
     InBuf<double> hopvec, lam, vab, e_rel;
-    DevBuf<double> v_lat;
+    DevBuf<double> v_lat, i4l;
     DevBuf<unsigned> site_pack, neigh_pack, neigh2_pack;
     DevBuf<int> neigh2;
     bool compact = false;
@@ -1273,6 +1288,12 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
                 check_launch(ctx, "neigh_pack_kernel");
             }
             {
+                const int nl = d->n_class * d->nn;
+                sys->i4l.alloc((size_t)nl);
+                inv4lambda_kernel<<<(nl + 127) / 128, 128, 0, s>>>(sys->lam.p, nl, sys->i4l.p);
+                check_launch(ctx, "inv4lambda_kernel");
+            }
+            {
                 const long long n2 = (long long)d->n_centres * d->nn * d->nn;
                 sys->neigh2.alloc((size_t)n2);
                 sys->neigh2_pack.alloc((size_t)n2);
@@ -1303,6 +1324,7 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             v.field_active = d->field_active;
             v.site_pack = sys->site_pack.p;
             v.neigh_pack = sys->neigh_pack.p;
+            v.i4l = sys->i4l.p;
             v.neigh2 = sys->neigh2.p;
             v.neigh2_pack = sys->neigh2_pack.p;
             v.n_basis = d->n_basis; v.sx = d->size[0]; v.sy = d->size[1]; v.sz = d->size[2];
