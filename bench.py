@@ -397,6 +397,10 @@ def main():
         peak, peak_src = measured_peaks()
         bstep = b_step_bytes(n_proc, C_)
         per_launch_bytes = bstep * nt * S
+        # bytes the incremental formulation actually gathers per step (8 B elements): untouched
+        # carriers 2+2nn each, every carrier nn+1 for the moved carrier's rebuild, + B_step/R
+        R_ = max(args.refresh, 1)
+        touched = bstep if R_ == 1 else 8 * ((C_ - 1) * (2 + 2 * nn) + C_ * (nn + 1) + 2 * nn + 2) + bstep // R_
         k_ms = kern_ms / args.steps
         achieved = per_launch_bytes / (k_ms * 1e-3) / 1e9
         line = {
@@ -421,9 +425,12 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': profiled_traffic(),
-                         'kernel': 'kmc_step_kernel<256>', 'kernel_ms_per_launch': k_ms,
+                         'kernel': ('kmc_step_carrier_kernel<64,4>' if (C_ == 64 and nn == 4) else 'kmc_step_kernel'),
+                         'kernel_ms_per_launch': k_ms,
                          'algorithmic_bytes_per_launch': per_launch_bytes,
                          'bytes_per_kmc_step': bstep, 'peak_source': peak_src,
+                         'touched_bytes_per_kmc_step': touched,
+                         'touched_achieved': touched * nt * S / (k_ms * 1e-3) / 1e9,
                          'note': 'algorithmic bytes are those of the STATELESS formulation (SURVEY 8d); '
                                  'with refresh_interval>1 the kernel touches ~22x fewer bytes, so frac '
                                  'can exceed 1; see stateless for the like-for-like figure'},
