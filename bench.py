@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument('--size', type=int, nargs=3, default=[10, 10, 10])
     ap.add_argument('--carriers', type=int, default=64)
     ap.add_argument('--traj-per-gpu', type=int, default=512)
-    ap.add_argument('--kmc-steps', type=int, default=4096, help='KMC steps per trajectory per bench step')
+    ap.add_argument('--kmc-steps', type=int, default=8192, help='KMC steps per trajectory per bench step')
     ap.add_argument('--refresh', type=int, default=256,
                     help='1 = stateless rate evaluation; R>1 = incremental updates, full re-gather every R')
     ap.add_argument('--n-path', type=int, default=101, help='rows of the recorded time grid')
