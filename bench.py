@@ -286,6 +286,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    kernel_names = {}
+
     def timed_run(refresh, steps, warmup):
         ens = K.KmcEnsemble(system, occ, dt_grid=dt_grid, n_path=args.n_path, step_limit=10 ** 12,
                             stop_at_grid_end=False, rng_mode=nat.RNG_PHILOX, seed=seed, traj_id0=traj_id0,
@@ -306,6 +308,7 @@ def main():
         clocks = sampler.stop() if sampler else None
         kern_ms = ctx.total_kernel_ms(nat.KC_KMC_STEP)
         launches = ctx.launch_count() - l0
+        kernel_names[refresh] = ens.last_kernel()
         return ens, wall, kern_ms, launches, clocks
 
     ens, wall, kern_ms, launches, clocks = timed_run(args.refresh, args.steps, args.warmup)
@@ -425,7 +428,7 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': profiled_traffic(),
-                         'kernel': ('kmc_step_carrier_kernel<64,4>' if (C_ == 64 and nn == 4) else 'kmc_step_kernel'),
+                         'kernel': kernel_names.get(args.refresh),
                          'kernel_ms_per_launch': k_ms,
                          'algorithmic_bytes_per_launch': per_launch_bytes,
                          'bytes_per_kmc_step': bstep, 'peak_source': peak_src,

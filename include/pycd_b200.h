@@ -192,6 +192,14 @@ int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t *n_steps, d
 int pycd_kmc_read_energy(pycd_kmc_ensemble *ens, double *energy_grid, double *dg0_grid);
 /* device pointer of the resident displacement grid (input of pycd_msd without a copy) */
 int pycd_kmc_unwrapped_device(pycd_kmc_ensemble *ens, const double **dev_ptr);
+/* Diagnostics: name of the step kernel the last pycd_kmc_advance launched (NUL-terminated,
+ * truncated to n bytes), and whether the UNIT_ROWS system carries the lattice-stencil tables
+ * (one table entry H[b_a][cell_y - cell_a][b_y][slot] = P[n_slot(a), y] - P[a, y] per carrier
+ * pair: the row difference of core.py:2004-2008 precomputed under translation symmetry).
+ * why: reason when unavailable. */
+int pycd_kmc_last_kernel(pycd_kmc_ensemble *ens, char *buf, int32_t n);
+int pycd_kmc_system_stencil(pycd_kmc_system *sys, int32_t *available, int64_t *table_bytes, char *why,
+                            int32_t n);
 
 /* ---- MSD --------------------------------------------------------------- */
 /* Replaces the lag loop of Analysis.compute_msd (core.py:2996-3022):

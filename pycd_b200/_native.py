@@ -39,7 +39,7 @@ def needs_build():
     if not LIB_PATH.exists():
         return True
     t = LIB_PATH.stat().st_mtime
-    deps = [CSRC_DIR / s for s in SOURCES] + [CSRC_DIR / 'common.cuh',
+    deps = [CSRC_DIR / s for s in SOURCES] + [CSRC_DIR / 'common.cuh', CSRC_DIR / 'kmc_stencil.cuh',
                                               PKG_DIR.parent / 'include' / 'pycd_b200.h']
     return any(d.stat().st_mtime > t for d in deps if d.exists())
 
@@ -126,6 +126,9 @@ _SIGNATURES = {
     'pycd_kmc_read': (C.c_int, [C.c_void_p] + [C.c_void_p] * 8),
     'pycd_kmc_read_energy': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pycd_kmc_unwrapped_device': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'pycd_kmc_last_kernel': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    'pycd_kmc_system_stencil': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_char_p,
+                                          C.c_int32]),
     'pycd_msd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                            C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }

@@ -1214,6 +1214,8 @@ __global__ void neigh_pack_kernel(const int *neigh, const unsigned *site_pack, l
 
 }  // namespace pycd
 
+#include "kmc_stencil.cuh"
+
 using namespace pycd;
 
 struct pycd_kmc_system {
@@ -1228,6 +1230,14 @@ struct pycd_kmc_system {
     DevBuf<unsigned> site_pack, neigh_pack, neigh2_pack;
     DevBuf<int> neigh2;
     bool compact = false;
+    // lattice-stencil tables (kmc_stencil.cuh); stencil_why says why they are absent
+    StencilDev st{};
+    bool stencil_ok = false;
+    std::string stencil_why = "not built";
+    size_t st_smem = 0;
+    DevBuf<double> st_H, st_cst;
+    DevBuf<int> st_ctr_key, st_ctr_site, st_nbr_key, st_nbr_ctr, st_cb_all, st_nb_all, st_nb_cell;
+    DevBuf<unsigned> st_perm;
 };
 
 struct pycd_kmc_ensemble {
@@ -1237,10 +1247,156 @@ struct pycd_kmc_ensemble {
     DevBuf<double> t, disp, row, drift, rates, unwrapped, kT_traj, field_traj, energy, energy_grid, dg0_grid;
     std::vector<double> energy0;
     DevBuf<long long> start_idx, n_steps, near_tie, clamped;
+    std::string last_kernel;
 };
 
 // energy outputs at t = 0: energy_array[0] = initial energy, everything else 0 (core.py:2715-2718, 2782-2783)
 static void arm_energy(pycd_kmc_ensemble *ens, cudaStream_t s);
+
+// Builds the lattice-stencil tables of kmc_stencil.cuh for the unit-rows layout.  Throws Error
+// with the reason when the system does not qualify (the caller then keeps the gather kernels):
+// the tables need centre = cell*ncb + basis numbering, periodic site classes / site energies, and
+// neighbour lists that are translations of those of unit cell 0 up to a permutation inside a
+// hop-distance class.
+static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, cudaStream_t s)
+{
+    pycd_ctx *ctx = sys->ctx;
+    const int nn = d->nn, nb = d->n_basis;
+    const long long n = d->n_sites, nc = d->n_centres;
+    const int sx = d->size[0], sy = d->size[1], sz = d->size[2];
+    const long long cells = (long long)sx * sy * sz;
+    auto need = [](bool ok, const char *why) { if (!ok) throw Error(why); };
+    need(nn <= 8, "more than 8 neighbour slots");
+    need(nc < (1 << 24) && nc % cells == 0, "centre count is not a multiple of the cell count");
+    const int ncb = (int)(nc / cells);
+    need(ncb >= 1 && ncb <= 127, "more than 127 carrier sites per unit cell");
+    const int nnp = (nn + 3) & ~3;
+    const int wx = 2 * sx - 1, wy = 2 * sy - 1, wz = 2 * sz - 1;
+    const long long n_delta = (long long)wx * wy * wz;
+    const long long rs = n_delta * ncb, entries = rs * ncb;
+    double max_mb = 96.0;
+    if (const char *e = getenv("PYCD_STENCIL_MAX_MB")) max_mb = atof(e);
+    need(entries < (1ll << 30) && (double)entries * nnp * 8.0 <= max_mb * 1048576.0,
+         "stencil table larger than PYCD_STENCIL_MAX_MB");
+    const size_t smem = (size_t)ncb * ST_ROWS * nn * sizeof(double);
+    need(smem <= 32 * 1024, "constant table does not fit in shared memory");
+
+    std::vector<int> neigh((size_t)nc * nn), site_centre((size_t)n), site_class((size_t)n);
+    std::vector<double> hop((size_t)nc * nn * 3), e_rel((size_t)n), lam((size_t)d->n_class * nn),
+        vab((size_t)d->n_class * nn);
+    PYCD_CUDA(cudaStreamSynchronize(s));
+    PYCD_CUDA(cudaMemcpy(neigh.data(), sys->neigh.p, sizeof(int) * neigh.size(), cudaMemcpyDeviceToHost));
+    PYCD_CUDA(cudaMemcpy(site_centre.data(), sys->site_centre.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    PYCD_CUDA(cudaMemcpy(site_class.data(), sys->site_class.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    PYCD_CUDA(cudaMemcpy(hop.data(), sys->hopvec.p, sizeof(double) * hop.size(), cudaMemcpyDeviceToHost));
+    PYCD_CUDA(cudaMemcpy(e_rel.data(), sys->e_rel.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    PYCD_CUDA(cudaMemcpy(lam.data(), sys->lam.p, sizeof(double) * lam.size(), cudaMemcpyDeviceToHost));
+    PYCD_CUDA(cudaMemcpy(vab.data(), sys->vab.p, sizeof(double) * vab.size(), cudaMemcpyDeviceToHost));
+
+    std::vector<int> ctr_site((size_t)nc, -1);
+    for (long long i = 0; i < n; ++i) {
+        const int e = site_centre[i];
+        if (e < 0) continue;
+        need(e < nc && ctr_site[e] < 0, "site_centre is not a bijection onto the centres");
+        ctr_site[e] = (int)i;
+    }
+    std::vector<int> cb_all(ncb);
+    for (int b = 0; b < ncb; ++b) {
+        need(ctr_site[b] >= 0 && ctr_site[b] < nb, "centres of unit cell 0 are not numbered first");
+        cb_all[b] = ctr_site[b];
+    }
+    for (long long e = 0; e < nc; ++e)
+        need(ctr_site[e] == (e / ncb) * nb + cb_all[e % ncb], "centre numbering is not cell*ncb + basis");
+    for (long long i = 0; i < n; ++i)
+        need(site_class[i] == site_class[i % nb] && e_rel[i] == e_rel[i % nb],
+             "site classes / relative site energies are not lattice periodic");
+
+    auto cell_xyz = [&](long long cell, int *c) {
+        c[2] = (int)(cell % sz); c[1] = (int)((cell / sz) % sy); c[0] = (int)(cell / ((long long)sz * sy));
+    };
+    auto key_of = [&](long long e) {
+        int c[3];
+        cell_xyz(e / ncb, c);
+        return (int)((((long long)c[0] * wy + c[1]) * wz + c[2]) * ncb + e % ncb);
+    };
+    // canonical directions of a basis site: the slots of its copy in unit cell 0
+    std::vector<int> nb_all((size_t)ncb * nn), nb_cell((size_t)ncb * nn * 3);
+    for (int b = 0; b < ncb; ++b)
+        for (int k = 0; k < nn; ++k) {
+            const int ns = neigh[(size_t)b * nn + k];
+            need(ns >= 0 && ns < n && site_centre[ns] >= 0, "neighbour is not a carrier site");
+            nb_all[b * nn + k] = ns % nb;
+            cell_xyz(ns / nb, &nb_cell[(size_t)(b * nn + k) * 3]);
+        }
+    std::vector<int> ctr_key((size_t)nc), nbr_key((size_t)nc * nn), nbr_ctr((size_t)nc * nn);
+    std::vector<unsigned> perm((size_t)nc);
+    const int size[3] = {sx, sy, sz};
+    for (long long e = 0; e < nc; ++e) {
+        const int b = (int)(e % ncb);
+        int ec[3];
+        cell_xyz(e / ncb, ec);
+        ctr_key[e] = key_of(e);
+        const int cls = site_class[ctr_site[e]];
+        need(cls >= 0 && cls < d->n_class, "bad site class");
+        unsigned used = 0, pm = 0;
+        for (int k = 0; k < nn; ++k) {
+            const int ns = neigh[(size_t)e * nn + k];
+            need(ns >= 0 && ns < n && site_centre[ns] >= 0, "neighbour is not a carrier site");
+            int c2[3], rel[3];
+            cell_xyz(ns / nb, c2);
+            for (int a = 0; a < 3; ++a) rel[a] = ((c2[a] - ec[a]) % size[a] + size[a]) % size[a];
+            const double *hv = &hop[((size_t)e * nn + k) * 3];
+            int found = -1;
+            for (int dd = 0; dd < nn && found < 0; ++dd) {
+                if (used & (1u << dd)) continue;
+                const int *cc = &nb_cell[(size_t)(b * nn + dd) * 3];
+                if (nb_all[b * nn + dd] != ns % nb || cc[0] != rel[0] || cc[1] != rel[1] || cc[2] != rel[2]) continue;
+                if (lam[cls * nn + dd] != lam[cls * nn + k] || vab[cls * nn + dd] != vab[cls * nn + k]) continue;
+                const double *h0 = &hop[((size_t)b * nn + dd) * 3];
+                bool close = true;
+                for (int a = 0; a < 3; ++a) close = close && std::fabs(hv[a] - h0[a]) <= 1e-9 * (1.0 + std::fabs(h0[a]));
+                if (close) found = dd;
+            }
+            need(found >= 0, "neighbour lists are not translations of those of unit cell 0");
+            used |= 1u << found;
+            pm |= (unsigned)k << (4 * found);
+            const int e2 = site_centre[ns];
+            nbr_key[(size_t)e * nn + k] = key_of(e2);
+            nbr_ctr[(size_t)e * nn + k] = e2 | ((e2 % ncb) << 24);
+        }
+        perm[e] = pm;
+    }
+
+    auto up_i = [&](DevBuf<int> &b, const std::vector<int> &v) {
+        b.alloc(v.size());
+        PYCD_CUDA(cudaMemcpyAsync(b.p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, s));
+    };
+    up_i(sys->st_ctr_key, ctr_key); up_i(sys->st_ctr_site, ctr_site); up_i(sys->st_nbr_key, nbr_key);
+    up_i(sys->st_nbr_ctr, nbr_ctr); up_i(sys->st_cb_all, cb_all); up_i(sys->st_nb_all, nb_all);
+    up_i(sys->st_nb_cell, nb_cell);
+    sys->st_perm.alloc(perm.size());
+    PYCD_CUDA(cudaMemcpyAsync(sys->st_perm.p, perm.data(), sizeof(unsigned) * perm.size(), cudaMemcpyHostToDevice, s));
+    sys->st_H.alloc((size_t)entries * nnp);
+    sys->st_cst.alloc((size_t)ncb * ST_ROWS * nn);
+    stencil_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(
+        sys->P.p, n, nb, sx, sy, sz, ncb, nn, nnp, sys->st_cb_all.p, sys->st_nb_all.p, sys->st_nb_cell.p, sys->st_H.p);
+    check_launch(ctx, "stencil_table_kernel");
+    stencil_const_kernel<<<(ncb * nn + 127) / 128, 128, 0, s>>>(
+        sys->P.p, n, nb, sy, sz, ncb, nn, sys->st_cb_all.p, sys->st_nb_all.p, sys->st_nb_cell.p, sys->v_lat.p,
+        sys->e_rel.p, sys->site_class.p, sys->lam.p, sys->vab.p, sys->i4l.p, d->q_carrier,
+        sys->st_cst.p);
+    check_launch(ctx, "stencil_const_kernel");
+    PYCD_CUDA(cudaStreamSynchronize(s));   // the host vectors above are read by the async copies
+    StencilDev &t = sys->st;
+    t.H = sys->st_H.p; t.ctr_key = sys->st_ctr_key.p; t.ctr_site = sys->st_ctr_site.p;
+    t.nbr_key = sys->st_nbr_key.p; t.nbr_ctr = sys->st_nbr_ctr.p; t.perm = sys->st_perm.p; t.cst = sys->st_cst.p;
+    t.ncb = ncb;
+    t.rs_p1 = (int)(rs + 1);
+    t.l0_ncb = (int)(((((long long)(sx - 1) * wy + (sy - 1)) * wz + (sz - 1))) * ncb);
+    sys->st_smem = smem;
+    sys->stencil_ok = true;
+    sys->stencil_why.clear();
+}
 
 extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc *d,
                                       pycd_kmc_system **out) {
@@ -1332,6 +1488,21 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             v.n_basis = d->n_basis; v.sx = d->size[0]; v.sy = d->size[1]; v.sz = d->size[2];
             sys->n_centres = d->n_centres;
             sys->n_class = d->n_class;
+            if (sys->compact) {
+                const char *off = getenv("PYCD_STENCIL");
+                if (off && std::string(off) == "0") {
+                    sys->stencil_why = "disabled by PYCD_STENCIL=0";
+                } else {
+                    try {
+                        setup_stencil(sys, d, s);
+                    } catch (const Error &e) {
+                        sys->stencil_ok = false;
+                        sys->stencil_why = e.what();
+                    }
+                }
+            } else {
+                sys->stencil_why = "dense layout";
+            }
         } catch (...) {
             delete sys;
             throw;
@@ -1545,9 +1716,26 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         // PYCD_KMC_VARIANT=process keeps the one-thread-per-process kernel for A/B measurements
         const char *kv = getenv("PYCD_KMC_VARIANT");
         const bool per_process = kv && std::string(kv) == "process";
+        const std::string variant = kv ? kv : "";
+        const bool use_stencil = cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 128 &&
+                                 (variant.empty() || variant == "stencil");
+        if (variant == "stencil" && !use_stencil)
+            throw Error("PYCD_KMC_VARIANT=stencil: stencil kernel unavailable (" +
+                        (ens->sys->stencil_ok ? std::string("shape not covered") : ens->sys->stencil_why) + ")");
+        ens->last_kernel = "kmc_step_kernel";
         int bs_force = 0;   // diagnostic: PYCD_KMC_BS forces the block size of the generic kernel
         if (const char *e = getenv("PYCD_KMC_BS")) bs_force = atoi(e);
-        if (bs_force == 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
+        if (use_stencil && bs_force == 0) {
+            // lattice-stencil kernel: one table entry per carrier pair (kmc_stencil.cuh)
+            const unsigned g = (unsigned)E.n_traj;
+            const size_t sm = ens->sys->st_smem;
+            if (E.C <= 32) kmc_step_stencil_kernel<32, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            else if (E.C <= 64) kmc_step_stencil_kernel<64, 4><<<g, 64, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            else kmc_step_stencil_kernel<128, 4><<<g, 128, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            check_launch(ctx, "kmc_step_stencil_kernel");
+            ens->last_kernel = "kmc_step_stencil_kernel<" + std::to_string(E.C <= 32 ? 32 : E.C <= 64 ? 64 : 128) + ",4>";
+        }
+        else if (bs_force == 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (bs_force == 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (bs_force == 128) launch_step<128>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (bs_force == 256) launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
@@ -1565,6 +1753,7 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
             else if (lean) kmc_step_carrier_kernel<64, 4, false, true><<<g, 64, 0, ctx->stream>>>(ens->sys->dev, E, A);
             else kmc_step_carrier_kernel<64, 4, false, false><<<g, 64, 0, ctx->stream>>>(ens->sys->dev, E, A);
             check_launch(ctx, "kmc_step_carrier_kernel");
+            ens->last_kernel = lean ? "kmc_step_carrier_kernel<64,4,lean>" : "kmc_step_carrier_kernel<64,4>";
         } else if (E.C == 64 && ens->sys->dev.nn == 4 && cp)   // one thread per process, fully specialised
             launch_step_impl<256, true, 64, 4>(ctx, ens->sys->dev, E, A, smem);
         else launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
@@ -1609,6 +1798,23 @@ extern "C" int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t 
         pull(clamped, ens->clamped.p, sizeof(long long) * nt);
         pull(rates, ens->rates.p, sizeof(double) * nt * E.n_proc);
         PYCD_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+extern "C" int pycd_kmc_last_kernel(pycd_kmc_ensemble *ens, char *buf, int32_t n) {
+    return guarded([&] {
+        PYCD_REQUIRE(ens && buf && n > 0, "NULL argument");
+        snprintf(buf, (size_t)n, "%s", ens->last_kernel.c_str());
+    });
+}
+
+extern "C" int pycd_kmc_system_stencil(pycd_kmc_system *sys, int32_t *available, int64_t *table_bytes, char *why,
+                                       int32_t n) {
+    return guarded([&] {
+        PYCD_REQUIRE(sys, "NULL system");
+        if (available) *available = sys->stencil_ok ? 1 : 0;
+        if (table_bytes) *table_bytes = (int64_t)(sys->st_H.n * sizeof(double));
+        if (why && n > 0) snprintf(why, (size_t)n, "%s", sys->stencil_why.c_str());
     });
 }
 

@@ -195,6 +195,12 @@ class KmcSystem:
             raise nat.NativeError('KMC system already destroyed')
         return self._h
 
+    def stencil_info(self):
+        """(available, table bytes, reason when unavailable) of the lattice-stencil tables."""
+        ok, nbytes, why = C.c_int32(), C.c_int64(), C.create_string_buffer(256)
+        nat.check(nat.lib().pycd_kmc_system_stencil(self.handle, C.byref(ok), C.byref(nbytes), why, 256))
+        return bool(ok.value), int(nbytes.value), why.value.decode()
+
     def v_lat(self):
         sc = self.run.supercell
         out = np.empty(sc.num_system_elements if self.layout == 'dense' else sc.n_per_cell)
@@ -340,6 +346,12 @@ class KmcEnsemble:
         g = np.empty((self.n_traj, self.n_path))
         nat.check(nat.lib().pycd_kmc_read_energy(self.handle, nat.ptr(e), nat.ptr(g)))
         return e, g
+
+    def last_kernel(self):
+        """Name of the step kernel the last advance launched."""
+        buf = C.create_string_buffer(128)
+        nat.check(nat.lib().pycd_kmc_last_kernel(self.handle, buf, 128))
+        return buf.value.decode()
 
     def unwrapped_device_ptr(self):
         p = C.c_void_p()

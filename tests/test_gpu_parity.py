@@ -290,6 +290,11 @@ def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
         pass
     got = ens.read(rates=True)
     eg, gg = ens.read_energy()
+    if layout == 'unit_rows':   # hop vectors of the fast geometry are exactly periodic: stencil path
+        assert system.stencil_info()[0], system.stencil_info()
+        assert ens.last_kernel().startswith('kmc_step_stencil_kernel<64')
+    else:
+        assert ens.last_kernel().startswith('kmc_step_carrier_kernel')
     ens.close()
     system.close()
     orc = O.KmcOracle(run, dense, rng_mode=1, seed=77, **kw)
@@ -301,6 +306,48 @@ def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
     one = orc.trajectory(occ[3], traj_id=3, energy0=e0[3])
     assert np.allclose(eg[3], one['energy_grid'], rtol=1e-11, atol=1e-13)
     assert np.allclose(gg[3], one['dg0_grid'], rtol=1e-9, atol=1e-15)
+
+
+@pytest.mark.parametrize('carriers', [5, 40, 64, 100])
+def test_stencil_kernel_equals_gather_kernels(ctx, hematite_64e, carriers, monkeypatch):
+    """The lattice-stencil kernel (one H[b_a][delta][b_y][slot] entry per carrier pair) against the
+    element-gather kernels on the same unit-row table: stateless mode bit-identical (rates, times,
+    events), incremental mode the same event sequence; carrier counts that leave idle threads."""
+    run64, p_unit, dense = hematite_64e
+    from pycd_b200.kmc import RunParameters
+    ex = H.load_example('hematite')
+    field = {'electric': {'active': 1, 'dir': [1, 0, 0], 'ld': 0, 'mag': 1e-3}}
+    run = RunParameters(run64.lattice, run64.supercell, run64.supercell.hop_neighbor_tables(), ex.sim['temp'],
+                        'full', 'full', ex.sim['t_final'], ex.sim['time_interval'], [carriers, 0], {},
+                        ex.sim['relative_energies'], field)
+    n_traj, steps = 8, 1600
+    occ = K.philox_initial_occupancy(run.tables, n_traj, carriers, seed=5)
+    kw = dict(dt_grid=run.time_interval / 4000, n_path=64, step_limit=steps, stop_at_grid_end=False)
+    out = {}
+    for variant in ('stencil', 'gather'):
+        monkeypatch.setenv('PYCD_STENCIL', '1' if variant == 'stencil' else '0')
+        system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+        assert system.stencil_info()[0] == (variant == 'stencil')
+        for refresh in (1, 16):
+            ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=5, refresh_interval=refresh, **kw)
+            res = ens.advance(steps, want_events=True, want_times=True)
+            state = ens.read(rates=True)
+            assert ens.last_kernel().startswith('kmc_step_stencil') == (variant == 'stencil')
+            out[variant, refresh] = (res, state)
+            ens.close()
+        system.close()
+    for refresh in (1, 16):
+        (ra, sa), (rb, sb) = out['stencil', refresh], out['gather', refresh]
+        assert np.array_equal(ra['events'], rb['events'])
+        assert np.array_equal(sa['occupancy'], sb['occupancy'])
+        assert np.array_equal(sa['unwrapped'], sb['unwrapped'])
+        if refresh == 1:
+            assert np.array_equal(sa['rates'], sb['rates'])
+            assert np.allclose(ra['times'], rb['times'], rtol=1e-13, atol=0)   # k_total: tree shapes differ
+            assert np.array_equal(sa['drift'], sb['drift'])
+        else:
+            assert np.allclose(sa['rates'], sb['rates'], rtol=1e-10, atol=0)
+            assert np.allclose(ra['times'], rb['times'], rtol=1e-11, atol=0)
 
 
 def test_64_carriers_replay_and_first_step_rates(ctx, hematite_64e):
