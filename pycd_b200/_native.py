@@ -48,7 +48,8 @@ def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> pycd_b200/libpycd_b200.so"""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+    extra = os.environ.get('PYCD_NVCC_EXTRA', '').split()   # e.g. -DPYCD_TRACE (tools/step_trace.py)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
           ['-o', str(LIB_PATH)] + [str(CSRC_DIR / s) for s in SOURCES]
     env = dict(os.environ)
     env.pop('CC', None)   # the image exports a gcc wrapper that nvcc must not pick up

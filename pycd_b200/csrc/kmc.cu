@@ -1717,23 +1717,36 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         const char *kv = getenv("PYCD_KMC_VARIANT");
         const bool per_process = kv && std::string(kv) == "process";
         const std::string variant = kv ? kv : "";
-        const bool use_stencil = cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 128 &&
-                                 (variant.empty() || variant == "stencil");
+        const bool use_stencil = cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 64 &&
+                                 (variant.empty() || variant == "stencil" || variant == "stencil_tpp" || variant == "stencil_1warp");
         if (variant == "stencil" && !use_stencil)
             throw Error("PYCD_KMC_VARIANT=stencil: stencil kernel unavailable (" +
                         (ens->sys->stencil_ok ? std::string("shape not covered") : ens->sys->stencil_why) + ")");
         ens->last_kernel = "kmc_step_kernel";
         int bs_force = 0;   // diagnostic: PYCD_KMC_BS forces the block size of the generic kernel
         if (const char *e = getenv("PYCD_KMC_BS")) bs_force = atoi(e);
-        if (use_stencil && bs_force == 0) {
-            // lattice-stencil kernel: one table entry per carrier pair (kmc_stencil.cuh)
+        if (use_stencil && bs_force == 0 && variant != "stencil_tpp") {
+            // one warp per trajectory over the lattice-stencil table (kmc_stencil.cuh)
             const unsigned g = (unsigned)E.n_traj;
             const size_t sm = ens->sys->st_smem;
-            if (E.C <= 32) kmc_step_stencil_kernel<32, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            else if (E.C <= 64) kmc_step_stencil_kernel<64, 4><<<g, 64, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            else kmc_step_stencil_kernel<128, 4><<<g, 128, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            check_launch(ctx, "kmc_step_stencil_kernel");
-            ens->last_kernel = "kmc_step_stencil_kernel<" + std::to_string(E.C <= 32 ? 32 : E.C <= 64 ? 64 : 128) + ",4>";
+            // small ensembles (a few trajectories per SM) are bound by the latency of a step: two warps
+            // per trajectory; large ones by instructions per step: one warp, two carriers per lane
+            const bool wide = E.C > 32 && E.n_traj <= 4ll * ctx->n_sm && variant != "stencil_1warp";
+            if (E.C <= 32) kmc_step_warp_kernel<1, 1, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            else if (wide) kmc_step_warp_kernel<2, 1, 4><<<g, 64, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            else kmc_step_warp_kernel<1, 2, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            const int nwc = wide ? 2 : 1, cpl = (E.C <= 32 || wide) ? 1 : 2;
+            check_launch(ctx, "kmc_step_warp_kernel");
+            ens->last_kernel = "kmc_step_warp_kernel<" + std::to_string(nwc) + "," + std::to_string(cpl) + ",4>";
+        }
+        else if (use_stencil && bs_force == 0) {
+            // one thread per process + a service warp over the same table (latency-optimal for small ensembles)
+            const unsigned g = (unsigned)E.n_traj;
+            const size_t sm = ens->sys->st_smem;
+            if (E.C <= 32) kmc_step_tpp_kernel<32, 4><<<g, 32 * 4 + 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            else kmc_step_tpp_kernel<64, 4><<<g, 64 * 4 + 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            check_launch(ctx, "kmc_step_tpp_kernel");
+            ens->last_kernel = "kmc_step_tpp_kernel<" + std::to_string(E.C <= 32 ? 32 : 64) + ",4>";
         }
         else if (bs_force == 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (bs_force == 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
@@ -1800,6 +1813,14 @@ extern "C" int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t 
         PYCD_CUDA(cudaStreamSynchronize(s));
     });
 }
+
+#ifdef PYCD_TRACE
+extern "C" int pycd_debug_trace(long long *out) {
+    return guarded([&] {
+        PYCD_CUDA(cudaMemcpyFromSymbol(out, g_st_trace, sizeof(long long) * 256 * 16 * 16));
+    });
+}
+#endif
 
 extern "C" int pycd_kmc_last_kernel(pycd_kmc_ensemble *ens, char *buf, int32_t n) {
     return guarded([&] {

@@ -292,7 +292,7 @@ def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
     eg, gg = ens.read_energy()
     if layout == 'unit_rows':   # hop vectors of the fast geometry are exactly periodic: stencil path
         assert system.stencil_info()[0], system.stencil_info()
-        assert ens.last_kernel().startswith('kmc_step_stencil_kernel<64')
+        assert ens.last_kernel().startswith('kmc_step_warp_kernel<')
     else:
         assert ens.last_kernel().startswith('kmc_step_carrier_kernel')
     ens.close()
@@ -308,7 +308,7 @@ def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
     assert np.allclose(gg[3], one['dg0_grid'], rtol=1e-9, atol=1e-15)
 
 
-@pytest.mark.parametrize('carriers', [5, 40, 64, 100])
+@pytest.mark.parametrize('carriers', [5, 33, 64])
 def test_stencil_kernel_equals_gather_kernels(ctx, hematite_64e, carriers, monkeypatch):
     """The lattice-stencil kernel (one H[b_a][delta][b_y][slot] entry per carrier pair) against the
     element-gather kernels on the same unit-row table: stateless mode bit-identical (rates, times,
@@ -332,7 +332,7 @@ def test_stencil_kernel_equals_gather_kernels(ctx, hematite_64e, carriers, monke
             ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=5, refresh_interval=refresh, **kw)
             res = ens.advance(steps, want_events=True, want_times=True)
             state = ens.read(rates=True)
-            assert ens.last_kernel().startswith('kmc_step_stencil') == (variant == 'stencil')
+            assert ens.last_kernel().startswith(('kmc_step_stencil', 'kmc_step_warp')) == (variant == 'stencil')
             out[variant, refresh] = (res, state)
             ens.close()
         system.close()
