@@ -1278,7 +1278,7 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
     if (const char *e = getenv("PYCD_STENCIL_MAX_MB")) max_mb = atof(e);
     need(entries < (1ll << 30) && (double)entries * nnp * 8.0 <= max_mb * 1048576.0,
          "stencil table larger than PYCD_STENCIL_MAX_MB");
-    const size_t smem = (size_t)ncb * ST_ROWS * nn * sizeof(double);
+    const size_t smem = (size_t)ncb * (ST_ROWS + 3) * nn * sizeof(double);   // raw rows + folded constants
     need(smem <= 32 * 1024, "constant table does not fit in shared memory");
 
     std::vector<int> neigh((size_t)nc * nn), site_centre((size_t)n), site_class((size_t)n);

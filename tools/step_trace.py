@@ -53,7 +53,7 @@ def main():
     tr = out.reshape(256, 16, 16)
     n_warps = 1 if warp_kernel else 9
     steps = slice(8, 250)
-    for w in ([0] if warp_kernel else [0, 3, 7, 8]):
+    for w in ([0, 1] if warp_kernel else [0, 3, 7, 8]):
         t = tr[steps, w, :16].astype(np.float64)
         t0 = tr[steps, 0, 0].astype(np.float64)[:, None]
         print(f'warp {w}: mean cycles since the step top of warp 0')
