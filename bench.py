@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument('--size', type=int, nargs=3, default=[10, 10, 10])
     ap.add_argument('--carriers', type=int, default=64)
     ap.add_argument('--traj-per-gpu', type=int, default=512)
-    ap.add_argument('--kmc-steps', type=int, default=8192, help='KMC steps per trajectory per bench step')
+    ap.add_argument('--kmc-steps', type=int, default=16384, help='KMC steps per trajectory per bench step')
     ap.add_argument('--refresh', type=int, default=256,
                     help='1 = stateless rate evaluation; R>1 = incremental updates, full re-gather every R')
     ap.add_argument('--n-path', type=int, default=101, help='rows of the recorded time grid')
@@ -90,50 +90,75 @@ def host_cores():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons sampled every 20 ms DURING the timed region (NVML in a thread;
+    falls back to one `nvidia-smi` query when the bindings are missing)."""
+    BITS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, period=0.02):
+        self.sm, self.mx, self.reasons, self.power = [], None, set(), []
+        self.index, self.period = index, period
+        self._stop = threading.Event()
+        self.thread = None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self._stop.wait(self.period)
 
     def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
+        if self.nv is None:
+            return self._smi_once()
+        self._stop.set()
+        self.thread.join(timeout=2)
         try:
-            self.proc.wait(timeout=5)
+            self._sample()
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for k, nme in enumerate(names):
-                if r[3 + k].lower().startswith('active'):
-                    reasons.add(nme)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+            pass
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.mx,
+                'samples': len(self.sm), 'power_w_max': max(self.power) if self.power else None,
+                'reasons': sorted(self.reasons), 'how': 'NVML every 20 ms inside the timed region'}
+
+    def _smi_once(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}',
+                                  '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=20).stdout
+            r = [x.strip() for x in out.strip().split(',')]
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            return {'sm_mhz': float(r[0]), 'sm_max_mhz': float(r[1]), 'samples': 1,
+                    'reasons': [n for n, v in zip(names, r[2:]) if v.lower().startswith('active')],
+                    'how': 'one nvidia-smi query after the timed region (NVML bindings unavailable)'}
+        except Exception:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'samples': 0, 'reasons': ['nvidia-smi unavailable']}
 
 
 def measured_peaks():
@@ -403,7 +428,13 @@ def main():
         # bytes the incremental formulation actually gathers per step (8 B elements): untouched
         # carriers 2+2nn each, every carrier nn+1 for the moved carrier's rebuild, + B_step/R
         R_ = max(args.refresh, 1)
-        touched = bstep if R_ == 1 else 8 * ((C_ - 1) * (2 + 2 * nn) + C_ * (nn + 1) + 2 * nn + 2) + bstep // R_
+        kname = kernel_names.get(args.refresh) or ''
+        if 'warp' in kname or 'tpp' in kname:
+            # lattice-stencil table: one 8*nn-byte entry per (carrier, other carrier) pair; incremental
+            # mode reads 3 entries per carrier per step + the full C x C re-gather every R steps
+            touched = 8 * nn * C_ * C_ if R_ == 1 else 8 * nn * (3 * C_ + 2) + 8 * nn * C_ * C_ // R_
+        else:
+            touched = bstep if R_ == 1 else 8 * ((C_ - 1) * (2 + 2 * nn) + C_ * (nn + 1) + 2 * nn + 2) + bstep // R_
         k_ms = kern_ms / args.steps
         achieved = per_launch_bytes / (k_ms * 1e-3) / 1e9
         line = {
@@ -414,7 +445,7 @@ def main():
             'config': {'workload': f'Hematite {args.size[0]}x{args.size[1]}x{args.size[2]} supercell '
                                    f'(N={N}), {C_} electrons, {nt} trajectories/GPU '
                                    f'({world * nt} total), Philox draws, fixed-step mode',
-                       'kmc_steps_per_step': S, 'n_proc': n_proc, 'refresh_interval': args.refresh, 'p_layout': 'dense N x N' if args.dense else 'unit-cell rows (n_per_cell x N) + lattice translation',
+                       'kmc_steps_per_step': S, 'n_proc': n_proc, 'refresh_interval': args.refresh, 'p_layout': 'dense N x N' if args.dense else 'unit-cell rows (n_per_cell x N) + lattice translation; step kernel reads the row-difference stencil table built from them',
                        'time_grid_rows': args.n_path,
                        'l2_policy': 'L2 flushed (512 MB write) between timed iterations' + (f'; dense array {N * N * 8 / 1e9:.1f} GB > L2' if args.dense else '; the unit-row table is re-fetched from HBM after each flush'),
                        'parallelism': f'trajectories sharded over {world} GPU(s), no data-path collective'},
@@ -434,16 +465,19 @@ def main():
                          'bytes_per_kmc_step': bstep, 'peak_source': peak_src,
                          'touched_bytes_per_kmc_step': touched,
                          'touched_achieved': touched * nt * S / (k_ms * 1e-3) / 1e9,
-                         'note': 'algorithmic bytes are those of the STATELESS formulation (SURVEY 8d); '
-                                 'with refresh_interval>1 the kernel touches ~22x fewer bytes, so frac '
-                                 'can exceed 1; see stateless for the like-for-like figure'},
+                         'note': 'algorithmic bytes are those of the STATELESS gather formulation (SURVEY 8d: '
+                                 '8*n_proc*(2C+6)+4*n_proc per KMC step); the kernel reads a precomputed '
+                                 'row-difference table (one 32-byte entry per carrier pair) and, with '
+                                 'refresh_interval>1, patches cached sums, so it touches touched_bytes_per_kmc_step '
+                                 'and frac exceeds 1; the step is bound by the latency of its dependency chain '
+                                 '(DESIGN.md 4.3), see stateless for the like-for-like figure'},
             'cpu_baseline': cpu,
             'ewald': ewald_info, 'msd': msd_info, 'near_tie_fallbacks': near_tie,
         }
         if stateless:
             a1 = per_launch_bytes / (stateless['kernel_ms_per_launch'] * 1e-3) / 1e9
             line['stateless'] = {'value': stateless['value'], 'kernel_ms_per_launch': stateless['kernel_ms_per_launch'],
-                                 'roofline_achieved': a1, 'roofline_frac': a1 / peak}
+                                 'roofline_achieved': a1, 'roofline_frac': a1 / peak, 'kernel': kernel_names.get(1)}
         print(json.dumps(line))
     if dist:
         dist.barrier()
