@@ -1718,14 +1718,14 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         const bool per_process = kv && std::string(kv) == "process";
         const std::string variant = kv ? kv : "";
         const bool use_stencil = cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 64 &&
-                                 (variant.empty() || variant == "stencil" || variant == "stencil_tpp" || variant == "stencil_1warp");
+                                 (variant.empty() || variant == "stencil" || variant == "stencil_1warp");
         if (variant == "stencil" && !use_stencil)
             throw Error("PYCD_KMC_VARIANT=stencil: stencil kernel unavailable (" +
                         (ens->sys->stencil_ok ? std::string("shape not covered") : ens->sys->stencil_why) + ")");
         ens->last_kernel = "kmc_step_kernel";
         int bs_force = 0;   // diagnostic: PYCD_KMC_BS forces the block size of the generic kernel
         if (const char *e = getenv("PYCD_KMC_BS")) bs_force = atoi(e);
-        if (use_stencil && bs_force == 0 && variant != "stencil_tpp") {
+        if (use_stencil && bs_force == 0) {
             // one warp per trajectory over the lattice-stencil table (kmc_stencil.cuh)
             const unsigned g = (unsigned)E.n_traj;
             const size_t sm = ens->sys->st_smem;
@@ -1738,15 +1738,6 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
             const int nwc = wide ? 2 : 1, cpl = (E.C <= 32 || wide) ? 1 : 2;
             check_launch(ctx, "kmc_step_warp_kernel");
             ens->last_kernel = "kmc_step_warp_kernel<" + std::to_string(nwc) + "," + std::to_string(cpl) + ",4>";
-        }
-        else if (use_stencil && bs_force == 0) {
-            // one thread per process + a service warp over the same table (latency-optimal for small ensembles)
-            const unsigned g = (unsigned)E.n_traj;
-            const size_t sm = ens->sys->st_smem;
-            if (E.C <= 32) kmc_step_tpp_kernel<32, 4><<<g, 32 * 4 + 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            else kmc_step_tpp_kernel<64, 4><<<g, 64 * 4 + 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            check_launch(ctx, "kmc_step_tpp_kernel");
-            ens->last_kernel = "kmc_step_tpp_kernel<" + std::to_string(E.C <= 32 ? 32 : 64) + ",4>";
         }
         else if (bs_force == 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (bs_force == 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);

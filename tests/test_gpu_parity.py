@@ -350,6 +350,39 @@ def test_stencil_kernel_equals_gather_kernels(ctx, hematite_64e, carriers, monke
             assert np.allclose(ra['times'], rb['times'], rtol=1e-11, atol=0)
 
 
+@pytest.mark.parametrize('variant', ['', 'stencil_1warp'])
+def test_stencil_sweep_conditions_time_grid(ctx, hematite_64e, variant, monkeypatch):
+    """Stencil step kernels (two warps per trajectory, and the one-warp shape large ensembles get) in
+    sweep mode: per-trajectory temperature and field, the reference's loop condition (run until the
+    time grid is full), state carried over several launches, incremental updates; every trajectory
+    equals the checker's run of its own condition."""
+    run, p_unit, dense = hematite_64e
+    monkeypatch.setenv('PYCD_KMC_VARIANT', variant)
+    n_traj = 6
+    occ = K.philox_initial_occupancy(run.tables, n_traj, 64, seed=9)
+    kTs = np.array([250, 300, 350, 400, 300, 350]) * constants.K2AUTEMP
+    fields = np.zeros((n_traj, 3))
+    fields[3:, 0] = 1e-3
+    kw = dict(dt_grid=run.time_interval / 200, n_path=96, stop_at_grid_end=True)
+    system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=9, refresh_interval=32, kT_traj=kTs,
+                        field_traj=fields, **kw)
+    launches = 0
+    while ens.advance_resident(256) > 0:
+        launches += 1
+    assert ens.last_kernel() == ('kmc_step_warp_kernel<1,2,4>' if variant else 'kmc_step_warp_kernel<2,1,4>')
+    got = ens.read()
+    ens.close()
+    system.close()
+    assert launches >= 2 and len(set(got['n_steps'])) > 1
+    for i in range(n_traj):
+        ref = O.KmcOracle(run, dense, kT=kTs[i], field=fields[i], rng_mode=1, seed=9, **kw).trajectory(occ[i], traj_id=i)
+        assert int(got['n_steps'][i]) == ref['n_steps']
+        assert np.array_equal(got['occupancy'][i], ref['occupancy'])
+        assert np.array_equal(got['unwrapped'][i], ref['unwrapped'])
+        assert np.allclose(got['drift'][i], ref['drift'], rtol=1e-9, atol=1e-300)
+
+
 def test_64_carriers_replay_and_first_step_rates(ctx, hematite_64e):
     import random
     run, p_unit, dense = hematite_64e
