@@ -1248,6 +1248,7 @@ struct pycd_kmc_ensemble {
     std::vector<double> energy0;
     DevBuf<long long> start_idx, n_steps, near_tie, clamped;
     std::string last_kernel;
+    long long n_active = -1;   // unfinished trajectories after the last advance (-1: all)
 };
 
 // energy outputs at t = 0: energy_array[0] = initial energy, everything else 0 (core.py:2715-2718, 2782-2783)
@@ -1650,6 +1651,7 @@ extern "C" int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *oc
         std::vector<long long> ones(nt, 1);
         PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
         E.traj_id0 = traj_id0;
+        ens->n_active = -1;
         arm_energy(ens, s);
         PYCD_CUDA(cudaStreamSynchronize(s));
     });
@@ -1731,7 +1733,9 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
             const size_t sm = ens->sys->st_smem;
             // small ensembles (a few trajectories per SM) are bound by the latency of a step: two warps
             // per trajectory; large ones by instructions per step: one warp, two carriers per lane
-            const bool wide = E.C > 32 && E.n_traj <= 4ll * ctx->n_sm && variant != "stencil_1warp";
+            // (finished trajectories leave their CTA at once, so the ACTIVE count decides)
+            const long long live = ens->n_active >= 0 ? ens->n_active : (long long)E.n_traj;
+            const bool wide = E.C > 32 && live <= 4ll * ctx->n_sm && variant != "stencil_1warp";
             if (E.C <= 32) kmc_step_warp_kernel<1, 1, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
             else if (wide) kmc_step_warp_kernel<2, 1, 4><<<g, 64, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
             else kmc_step_warp_kernel<1, 2, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
@@ -1769,10 +1773,11 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         PYCD_CUDA(cudaMemcpyAsync(done_h.data(), ens->done.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, s));
         PYCD_CUDA(cudaStreamSynchronize(s));
         tk.read();
-        if (n_active) {
+        {
             int64_t act = 0;
             for (int v : done_h) act += (v == 0);
-            *n_active = act;
+            ens->n_active = act;
+            if (n_active) *n_active = act;
         }
     });
 }
