@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PYCD_ABI_VERSION 1
+#define PYCD_ABI_VERSION 2
 
 typedef struct pycd_ctx pycd_ctx;
 typedef struct pycd_kmc_system pycd_kmc_system;
@@ -162,6 +162,15 @@ typedef struct {
     int32_t record_unwrapped;  /* 1: keep the (n_traj, n_path, 3C) displacement grid on the device */
     const double *energy0;     /* NULL, or (n_traj) system energy of the initial state (core.py:2778-2780):
                                   turns on the energy / delg_0 grids of output_data */
+    /* Doping hooks of Run.do_kmc_steps (core.py:2723-2776); all NULL / 0 for an undoped run.  The
+     * dopant distribution itself (site_indices.npy) comes from the reference's material_preprod. */
+    const double *e_rel_traj;  /* NULL or (n_traj, N): per-trajectory system_relative_energies with the
+                                  shell shifts of relative_energies['doping'] applied (core.py:2750-2764) */
+    int32_t n_dopant_max;      /* D: columns of the two arrays below */
+    const int32_t *dopant_site;/* NULL or (n_traj, D): dopant sites, -1 = unused entry */
+    const double *dopant_dq;   /* (n_traj, D): dopant charge minus the undoped lattice charge of the site
+                                  (charge_config, core.py:2553-2557); the device adds
+                                  sum_d dq_d P[s, d] to the trajectory's lattice potential */
 } pycd_kmc_ensemble_desc;
 
 int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ensemble_desc *desc,

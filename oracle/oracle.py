@@ -120,7 +120,9 @@ class KmcOracle:
     the CPU, literally (O(N) dot with the charge vector) or in the gather form."""
 
     def __init__(self, run, P, literal=False, kT=None, field=None, dt_grid=None, n_path=None,
-                 step_limit=0, stop_at_grid_end=True, rng_mode=0, seed=0):
+                 step_limit=0, stop_at_grid_end=True, rng_mode=0, seed=0, e_rel=None, q_lat=None):
+        # e_rel / q_lat: a doped trajectory's site energies and lattice charges (core.py:2723-2764,
+        # 2553-2557) in place of the undoped ones
         t = run.tables
         self.run = run
         self.a = dict(
@@ -131,8 +133,8 @@ class KmcOracle:
             hopvec=np.ascontiguousarray(t.hopvec, dtype=np.float64),
             lam=np.ascontiguousarray(t.lam, dtype=np.float64),
             vab=np.ascontiguousarray(t.vab, dtype=np.float64),
-            e_rel=np.ascontiguousarray(run.e_rel, dtype=np.float64),
-            q_lat=np.ascontiguousarray(run.q_lat, dtype=np.float64))
+            e_rel=np.ascontiguousarray(run.e_rel if e_rel is None else e_rel, dtype=np.float64),
+            q_lat=np.ascontiguousarray(run.q_lat if q_lat is None else q_lat, dtype=np.float64))
         self.a['v_lat'] = vlat(self.a['P'], self.a['q_lat'])
         p = KmcParams()
         p.n_sites = run.supercell.num_system_elements

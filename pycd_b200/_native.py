@@ -90,7 +90,9 @@ class KmcEnsembleDesc(C.Structure):
                 ('step_limit', C.c_int64), ('stop_at_grid_end', C.c_int32),
                 ('rng_mode', C.c_int32), ('seed', C.c_uint64), ('refresh_interval', C.c_int32),
                 ('kT_traj', C.c_void_p), ('field_traj', C.c_void_p),
-                ('record_unwrapped', C.c_int32), ('energy0', C.c_void_p)]
+                ('record_unwrapped', C.c_int32), ('energy0', C.c_void_p),
+                ('e_rel_traj', C.c_void_p), ('n_dopant_max', C.c_int32),
+                ('dopant_site', C.c_void_p), ('dopant_dq', C.c_void_p)]
 
 
 _lib = None

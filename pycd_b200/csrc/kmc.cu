@@ -33,7 +33,8 @@ struct SysDev {
     const double *vab;
     const double *i4l;        // 1/(4 lambda) per (class, slot)
     const double *e_rel;
-    const double *v_lat;      // dense: [N]; compact: [n_basis]
+    const double *v_lat;      // dense: [N]; compact: [n_basis] (doped trajectory: [N] either way)
+    int vlat_by_site;         // 1: v_lat is indexed by site in the compact layout too (doped trajectory)
     double qc, kT, vn;
     double field[3];
     int field_active;
@@ -57,6 +58,8 @@ struct EnsDev {
     double *rates;         // [n_traj][n_proc]
     const double *kT_traj;
     const double *field_traj;
+    const double *e_rel_traj;  // NULL or [n_traj][N]: a doped trajectory's site energies (core.py:2750-2764)
+    const double *v_lat_traj;  // NULL or [n_traj][N]: its lattice potential, dopant charges included
     double *unwrapped;     // [n_traj][n_path][3C] or NULL
     double *energy;        // [n_traj] current_state_energy, or NULL (energy outputs off)
     double *energy_grid;   // [n_traj][n_path]
@@ -169,7 +172,7 @@ __device__ __forceinline__ double ld_pair(const SysDev &S, const Site x, const S
 template <bool COMPACT>
 __device__ __forceinline__ double ld_vlat(const SysDev &S, const Site x)
 {
-    return __ldg(S.v_lat + (COMPACT ? (int)(x.pack & 255u) : x.idx));
+    return __ldg(S.v_lat + ((COMPACT && !S.vlat_by_site) ? (int)(x.pack & 255u) : x.idx));
 }
 
 // np.e ** y  (core.py:2047).  The reference raises the ROUNDED constant np.e =
@@ -284,10 +287,17 @@ struct StepCtl {
 // specialisation folds the shared-memory layout and the index divisions into constants.
 template <int BS, bool COMPACT, int CT, int NNT>
 __global__ void __launch_bounds__(BS, (BS >= 128) ? 1024 / BS : 1)
-kmc_step_kernel(SysDev S, EnsDev E, AdvanceArgs A)
+kmc_step_kernel(SysDev S_in, EnsDev E, AdvanceArgs A)
 {
     const int traj = blockIdx.x;
     const int tid = threadIdx.x;
+    // doped trajectory (core.py:2723-2776): its own site energies and lattice potential
+    SysDev S = S_in;
+    if (E.v_lat_traj) {
+        S.e_rel = E.e_rel_traj + (long long)traj * S_in.n_sites;
+        S.v_lat = E.v_lat_traj + (long long)traj * S_in.n_sites;
+        S.vlat_by_site = 1;
+    }
     const int C = CT ? CT : E.C;
     const int nn = NNT ? NNT : S.nn;
     const int n_proc = (CT && NNT) ? CT * NNT : E.n_proc;
@@ -1177,6 +1187,27 @@ static size_t kmc_smem_bytes(int n_proc, int C, int nn) {
 }
 
 // basis | x<<8 | y<<16 | z<<24 per site (site = cell*n_basis + basis, cell = (x*sy + y)*sz + z)
+// Lattice potential of doped trajectories: the dopant sites carry the dopant's charge instead of the
+// substituted ion's (charge_config, core.py:2553-2557), i.e. V_lat'[s] = V_lat[s] + sum_d dq_d P[s, d].
+template <bool COMPACT>
+__global__ void __launch_bounds__(256)
+vlat_doped_kernel(SysDev S, long long n_traj, int n_dop, const int *__restrict__ dsite,
+                  const double *__restrict__ ddq, double *__restrict__ out)
+{
+    const long long total = n_traj * S.n_sites;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long traj = i / S.n_sites;
+        const Site x = make_site<COMPACT>(S, (int)(i - traj * S.n_sites));
+        double v = ld_vlat<COMPACT>(S, x);
+        for (int d = 0; d < n_dop; ++d) {
+            const int site = dsite[traj * n_dop + d];
+            if (site >= 0) v = fma(ddq[traj * n_dop + d], ld_pair<COMPACT>(S, x, make_site<COMPACT>(S, site)), v);
+        }
+        out[i] = v;
+    }
+}
+
 __global__ void site_pack_kernel(unsigned *out, long long n, int nb, int sy, int sz)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1245,6 +1276,7 @@ struct pycd_kmc_ensemble {
     EnsDev dev{};
     DevBuf<int> occ, done;
     DevBuf<double> t, disp, row, drift, rates, unwrapped, kT_traj, field_traj, energy, energy_grid, dg0_grid;
+    DevBuf<double> e_rel_traj, v_lat_traj;   // doped ensembles only
     std::vector<double> energy0;
     DevBuf<long long> start_idx, n_steps, near_tie, clamped;
     std::string last_kernel;
@@ -1540,6 +1572,7 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
         PYCD_REQUIRE(d->refresh_interval >= 1, "refresh_interval must be >= 1");
         PYCD_REQUIRE(d->rng_mode == PYCD_RNG_REPLAY || d->rng_mode == PYCD_RNG_PHILOX, "bad rng_mode");
         PYCD_REQUIRE(d->stop_at_grid_end || d->step_limit > 0, "trajectory would never end");
+        PYCD_REQUIRE(!d->dopant_site || (d->n_dopant_max > 0 && d->dopant_dq), "dopant_site needs n_dopant_max and dopant_dq");
         pycd_ctx *ctx = sys->ctx;
         DeviceGuard g(ctx);
         const long long nt = d->n_traj;
@@ -1591,7 +1624,36 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
                 ens->field_traj.alloc((size_t)nt * 3);
                 PYCD_CUDA(cudaMemcpyAsync(ens->field_traj.p, d->field_traj, sizeof(double) * nt * 3, cudaMemcpyDefault, s));
             }
+            if (d->e_rel_traj || d->dopant_site) {   // doping hooks
+                const long long n = sys->dev.n_sites;
+                ens->e_rel_traj.alloc((size_t)nt * n);
+                if (d->e_rel_traj)
+                    PYCD_CUDA(cudaMemcpyAsync(ens->e_rel_traj.p, d->e_rel_traj, sizeof(double) * nt * n, cudaMemcpyDefault, s));
+                else
+                    for (long long i = 0; i < nt; ++i)
+                        PYCD_CUDA(cudaMemcpyAsync(ens->e_rel_traj.p + i * n, sys->dev.e_rel, sizeof(double) * n,
+                                                  cudaMemcpyDeviceToDevice, s));
+                const int nd = d->dopant_site ? d->n_dopant_max : 0;
+                DevBuf<int> dsite;
+                DevBuf<double> ddq;
+                if (nd > 0) {
+                    std::vector<int> site_h((size_t)nt * nd);
+                    PYCD_CUDA(cudaMemcpy(site_h.data(), d->dopant_site, sizeof(int) * nt * nd, cudaMemcpyDefault));
+                    for (int v : site_h) PYCD_REQUIRE(v >= -1 && v < n, "dopant site out of range");
+                    dsite.alloc((size_t)nt * nd);
+                    ddq.alloc((size_t)nt * nd);
+                    PYCD_CUDA(cudaMemcpyAsync(dsite.p, site_h.data(), sizeof(int) * nt * nd, cudaMemcpyHostToDevice, s));
+                    PYCD_CUDA(cudaMemcpyAsync(ddq.p, d->dopant_dq, sizeof(double) * nt * nd, cudaMemcpyDefault, s));
+                }
+                ens->v_lat_traj.alloc((size_t)nt * n);
+                const unsigned grid = (unsigned)std::min<long long>((nt * n + 255) / 256, 148ll * 16);
+                if (sys->compact) vlat_doped_kernel<true><<<grid, 256, 0, s>>>(sys->dev, nt, nd, dsite.p, ddq.p, ens->v_lat_traj.p);
+                else vlat_doped_kernel<false><<<grid, 256, 0, s>>>(sys->dev, nt, nd, dsite.p, ddq.p, ens->v_lat_traj.p);
+                check_launch(ctx, "vlat_doped_kernel");
+                PYCD_CUDA(cudaStreamSynchronize(s));   // dsite / ddq are released at the end of this block
+            }
             EnsDev &e = ens->dev;
+            e.e_rel_traj = ens->e_rel_traj.p; e.v_lat_traj = ens->v_lat_traj.p;
             e.energy = ens->energy.p; e.energy_grid = ens->energy_grid.p; e.dg0_grid = ens->dg0_grid.p;
             e.n_path = d->n_path;
             arm_energy(ens, s);
@@ -1719,7 +1781,10 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         const char *kv = getenv("PYCD_KMC_VARIANT");
         const bool per_process = kv && std::string(kv) == "process";
         const std::string variant = kv ? kv : "";
-        const bool use_stencil = cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 64 &&
+        // doped ensembles carry per-trajectory site tables: the lattice-stencil constants and the carrier
+        // kernel's lookups are per system, so they run on the generic gather kernel
+        const bool doped = E.v_lat_traj != nullptr;
+        const bool use_stencil = !doped && cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 64 &&
                                  (variant.empty() || variant == "stencil" || variant == "stencil_1warp");
         if (variant == "stencil" && !use_stencil)
             throw Error("PYCD_KMC_VARIANT=stencil: stencil kernel unavailable (" +
@@ -1750,7 +1815,7 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         else if (E.n_proc <= 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (E.n_proc <= 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (E.n_proc <= 128) launch_step<128>(ctx, cp, ens->sys->dev, E, A, smem);
-        else if (E.C == 64 && ens->sys->dev.nn == 4 && !per_process) {
+        else if (E.C == 64 && ens->sys->dev.nn == 4 && !per_process && !doped) {
             // the benchmark shape: one thread per carrier, process state in registers
             // between 4 and 8 CTAs per SM the 128-register variant keeps every trajectory resident in
             // one wave (measured +12 % at 1024 trajectories); beyond that both run in waves

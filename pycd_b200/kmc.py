@@ -13,6 +13,7 @@ import numpy as np
 
 from . import _native as nat
 from . import constants
+from .doping import DopingHooks
 from .tables import HopTables
 
 
@@ -22,7 +23,7 @@ class RunParameters:
 
     def __init__(self, lattice, supercell, hop_neighbor_list, temp, ion_charge_type,
                  species_charge_type, t_final, time_interval, species_count,
-                 initial_occupancy=None, relative_energies=None, external_field=None):
+                 initial_occupancy=None, relative_energies=None, external_field=None, doping=None):
         lat = lattice
         self.lattice, self.supercell = lattice, supercell
         self.species_count = np.asarray(species_count, dtype=int)
@@ -63,6 +64,8 @@ class RunParameters:
         unit_q = np.array([lat.charge_types[ion_charge_type][lat.element_types[i]]
                            for i in lat.element_type_index_list], dtype=float)
         self.q_lat = np.tile(unit_q, supercell.num_cells)
+        # doping hooks, core.py:1763-1781 (inactive unless num_dopants has a non-zero entry)
+        self.doping = DopingHooks(lat, doping, relative_energies, ion_charge_type)
         # electric field, core.py:1749-1761
         self.field_active = 0
         self.field = np.zeros(3)
@@ -77,25 +80,29 @@ class RunParameters:
                 self.field = ef['mag'] * (direction / np.linalg.norm(direction))
                 self.field_active = 1
 
-    def initial_energy(self, P, occupancy, alpha_per_angstrom):
+    def initial_energy(self, P, occupancy, alpha_per_angstrom, q_lat=None):
         """current_state_energy before the first step (core.py:2663-2667, 2773-2780):
-        ewald_neut + sum_ij q_i q_j P_ij with q = lattice charges + carriers.  alpha is the
-        value material_run re-reads from precomputed_array.log (1/angstrom)."""
+        ewald_neut + sum_ij q_i q_j P_ij with q = lattice charges (q_lat: a doped trajectory's)
+        + carriers.  alpha is the value material_run re-reads from precomputed_array.log
+        (1/angstrom)."""
         sc = self.supercell
         alpha = alpha_per_angstrom / constants.ANG2BOHR  # core.py:768-769
         system_charge = float(np.dot(self.species_count,
                                      self.lattice.species_charge_list[self.species_charge_type]))
         ewald_neut = -(np.pi * system_charge ** 2 / (2 * sc.system_volume * alpha))
-        q = self.q_lat.copy()
+        q = np.array(self.q_lat if q_lat is None else q_lat, dtype=np.float64, copy=True)
         np.add.at(q, np.asarray(occupancy, dtype=int), self.q_carrier)
         return ewald_neut + float(q @ (P @ q))
 
     # -- initial state -----------------------------------------------------------------
-    def initial_occupancy_from(self, rng):
-        """generate_initial_occupancy without doping (core.py:2483-2528): explicit sites
-        first, then rng.sample over the element's sites in ascending index."""
+    def initial_occupancy_from(self, rng, dopant_site_indices=None):
+        """generate_initial_occupancy (core.py:2483-2528): carriers started on dopant sites
+        (site_charge_initiation, doped runs only), then explicit sites, then rng.sample over the
+        element's sites in ascending index."""
         occ = []
         n = self.n_carriers
+        if self.doping.active:
+            occ, n = self.doping.initiation_sites(rng, self.species_type, n, dopant_site_indices or {})
         explicit = self.initial_occupancy.get(self.species_type) or []
         occ.extend(int(i) for i in explicit)
         n -= len(explicit)
@@ -224,7 +231,10 @@ class KmcEnsemble:
 
     def __init__(self, system, occupancy0, dt_grid=None, n_path=None, step_limit=0,
                  stop_at_grid_end=True, rng_mode=nat.RNG_REPLAY, seed=0, traj_id0=0,
-                 refresh_interval=1, kT_traj=None, field_traj=None, record_unwrapped=True, energy0=None):
+                 refresh_interval=1, kT_traj=None, field_traj=None, record_unwrapped=True, energy0=None,
+                 doping=None):
+        """doping: None or one doping.TrajectoryDoping per trajectory (core.py:2723-2776): the
+        trajectory's shifted site energies and the charges its dopant sites carry."""
         run = system.run
         self.system = system
         occ = np.ascontiguousarray(occupancy0, dtype=np.int32)
@@ -263,6 +273,25 @@ class KmcEnsemble:
             assert energy0.shape == (self.n_traj,)
             d.energy0 = nat.ptr(energy0)
             keep.append(energy0)
+        if doping is not None:
+            if len(doping) != self.n_traj:
+                raise ValueError('doping needs one entry per trajectory')
+            n_sites = run.supercell.num_system_elements
+            e_rel_traj = np.ascontiguousarray([t.e_rel for t in doping], dtype=np.float64)
+            assert e_rel_traj.shape == (self.n_traj, n_sites)
+            d.e_rel_traj = nat.ptr(e_rel_traj)
+            keep.append(e_rel_traj)
+            n_dop = max(len(t.sites) for t in doping)
+            if n_dop:
+                dsite = np.full((self.n_traj, n_dop), -1, dtype=np.int32)
+                ddq = np.zeros((self.n_traj, n_dop))
+                for i, t in enumerate(doping):
+                    dsite[i, :len(t.sites)] = t.sites
+                    ddq[i, :len(t.sites)] = t.dq
+                d.n_dopant_max = n_dop
+                d.dopant_site = nat.ptr(dsite)
+                d.dopant_dq = nat.ptr(ddq)
+                keep += [dsite, ddq]
         d.record_unwrapped = int(bool(record_unwrapped))
         self.record_unwrapped = bool(record_unwrapped)
         self._h = C.c_void_p()
@@ -371,12 +400,13 @@ class KmcEnsemble:
 
 
 def run_replay(system, rngs, occupancy0, chunk_steps=32768, want_times=True, want_events=False,
-               max_total_steps=None, energy0=None):
+               max_total_steps=None, energy0=None, doping=None):
     """Runs trajectories to the end of their time grid, feeding each one the continuing
     stream of its own Python MT19937 generator (u1 then u2 per step, core.py:2799-2802).
     Returns (state dict from KmcEnsemble.read, list of per-trajectory time arrays incl. the
     leading 0.0, list of per-trajectory event arrays or None)."""
-    ens = KmcEnsemble(system, occupancy0, rng_mode=nat.RNG_REPLAY, refresh_interval=1, energy0=energy0)
+    ens = KmcEnsemble(system, occupancy0, rng_mode=nat.RNG_REPLAY, refresh_interval=1, energy0=energy0,
+                      doping=doping)
     n_traj = ens.n_traj
     times = [[np.zeros(1)] for _ in range(n_traj)]
     events = [[] for _ in range(n_traj)]

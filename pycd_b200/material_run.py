@@ -35,8 +35,6 @@ def material_run(dst_path):
     if (dst_path / 'Run.log').exists() and not sim['over_write']:
         print('Simulation files already exists in the destination directory')
         return None
-    if sim.get('doping') and any(sim['doping'].get('num_dopants', [])):
-        raise NotImplementedError('doping is outside the accelerated path (SURVEY section 2)')
     opts = sim['b200']
     hop = load_hop_neighbor_list(inp / 'hop_neighbor_list.npy')
     alpha_log = _alpha_from_log(inp / 'precomputed_array.log', params.alpha)  # feeds the energy output only
@@ -46,7 +44,7 @@ def material_run(dst_path):
     run = kmc.RunParameters(lattice, supercell, hop, sim['temp'], sim['ion_charge_type'],
                             sim['species_charge_type'], sim['t_final'], sim['time_interval'],
                             sim['species_count'], sim['initial_occupancy'],
-                            sim['relative_energies'], sim['external_field'])
+                            sim['relative_energies'], sim['external_field'], sim.get('doping'))
     out_cfg = sim['output_data']
     want_energy = bool(out_cfg.get('energy', {}).get('write') or out_cfg.get('delg_0', {}).get('write'))
     if out_cfg['unwrapped_traj'].get('write_every_step'):
@@ -58,6 +56,25 @@ def material_run(dst_path):
     for d in traj_dirs:
         d.mkdir(parents=True, exist_ok=True)
 
+    # Doping hooks (core.py:2723-2776): every trajectory reads the site_indices.npy that the
+    # reference's material_preprod wrote (the dopant distribution itself is control plane and not
+    # regenerated here, unlike the reference's serial mode, which rewrites the same files).
+    doping = None
+    if run.doping.active:
+        doping = []
+        for d in traj_dirs:
+            path = run.doping.site_indices_path(d)
+            if not path.exists():
+                raise FileNotFoundError(f'{path}: doped runs need the site_indices.npy written by '
+                                        "PyCD's material_preprod (dopant distribution, core.py:2566-2645)")
+            doping.append(run.doping.load(np.load(path), run.e_rel, run.q_lat))
+
+    def traj_q_lat(i):
+        return doping[i].q_lat(run.q_lat) if doping else None
+
+    def traj_dopants(i):
+        return doping[i].dopant_site_indices if doping else None
+
     ctx = nat.default_context()
     system = kmc.KmcSystem(ctx, run, P)
     rng_kind = opts.get('rng', 'replay')
@@ -65,18 +82,21 @@ def material_run(dst_path):
     want_times = bool(out_cfg['time']['write'])
     if rng_kind == 'replay':
         rngs = [kmc.load_rnd_state(d / 'initial_rnd_state.dump') for d in traj_dirs]
-        occ = np.array([run.initial_occupancy_from(r) for r in rngs], dtype=np.int32)
-        energy0 = np.array([run.initial_energy(P, o, alpha_log) for o in occ]) if want_energy else None
+        occ = np.array([run.initial_occupancy_from(r, traj_dopants(i)) for i, r in enumerate(rngs)],
+                       dtype=np.int32)
+        energy0 = np.array([run.initial_energy(P, o, alpha_log, traj_q_lat(i)) for i, o in enumerate(occ)]) \
+            if want_energy else None
         state, times, _ = kmc.run_replay(system, rngs, occ, chunk_steps=chunk, want_times=want_times,
-                                         energy0=energy0)
+                                         energy0=energy0, doping=doping)
     elif rng_kind == 'philox':
         seed = int(sim['random_seed'])
         occ = kmc.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed)
         refresh = int(opts.get('refresh_interval', 1))
         chunk -= chunk % refresh
-        energy0 = np.array([run.initial_energy(P, o, alpha_log) for o in occ]) if want_energy else None
+        energy0 = np.array([run.initial_energy(P, o, alpha_log, traj_q_lat(i)) for i, o in enumerate(occ)]) \
+            if want_energy else None
         ens = kmc.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=seed, refresh_interval=refresh,
-                              energy0=energy0)
+                              energy0=energy0, doping=doping)
         pieces = [[np.zeros(1)] for _ in range(n_traj)]
         while True:
             res = ens.advance(chunk, want_times=want_times)

@@ -157,12 +157,78 @@ def energy_case():
                     'output_data': {'energy': {'write': 1}, 'delg_0': {'write': 1}}})
 
 
+def doped_case(tag, species_count, extra):
+    """Reference material_preprod + material_run with dopants (BVO, W on V sites): the doping
+    hooks of do_kmc_steps (core.py:2723-2776): per-trajectory site_indices.npy -> shifted
+    system_relative_energies, dopant charges in charge_config, site_charge_initiation."""
+    core = rh.load_reference()
+    from PyCD.material_preprod import material_preprod
+    from PyCD.material_run import material_run
+    work = rh.stage_example('BVO', TMP / tag, species_count=species_count, extra=extra)
+    material_preprod(work)
+    t0 = time.time()
+    material_run(work)
+    dt = time.time() - t0
+    sim = yaml.safe_load(open(work / 'simulation_parameters.yml'))
+    n_traj = int(sim['n_traj'])
+    out = {'species_count': np.asarray(species_count), 'n_traj': n_traj, 'sim_yaml': yaml.safe_dump(sim),
+           'example': 'BVO', 'ref_seconds': dt}
+    core, run, _ = reference_run_object(work)
+    total_steps = 0
+    for i in range(n_traj):
+        d = work / f'traj{i + 1}'
+        out[f'rnd_state_{i}'] = np.frombuffer((d / 'initial_rnd_state.dump').read_bytes(), dtype=np.uint8)
+        out[f'site_indices_{i}'] = np.load(d / 'site_indices.npy')
+        out[f'unwrapped_{i}'] = np.load(d / 'unwrapped_traj.npy')
+        td = np.load(d / 'time_data.npy')
+        out[f'time_{i}'] = td
+        total_steps += len(td) - 1
+        # first-step state and rates from the reference's own routines, doping hooks applied
+        # the way do_kmc_steps applies them (core.py:2723-2772)
+        si = out[f'site_indices_{i}']
+        dop = {}
+        for row in si[si[:, 3] == 0]:
+            dop.setdefault(run.dopant_element_types[row[1]], []).append(int(row[0]))
+        e_rel = np.copy(run.undoped_system_relative_energies)
+        for site, ti, _, shell in si:
+            sub = run.substitution_element_types[ti]
+            table = run.relative_energies['doping'][sub][ti]
+            if shell < len(table):
+                e_rel[site] += table[shell] * core.constants.EV2HARTREE
+        run.system_relative_energies = e_rel
+        core.rnd.setstate(pickle.load(open(d / 'initial_rnd_state.dump', 'rb')))
+        occ = run.generate_initial_occupancy(dop)
+        q = run.charge_config(occ, dop)
+        attrs = run.get_process_attributes(occ)
+        k_list, dg0, hopv = run.get_process_rates(attrs, q)
+        out[f'occ0_{i}'] = np.asarray(occ)
+        out[f'q0_{i}'] = np.asarray(q)[:, 0]
+        out[f'e_rel_{i}'] = e_rel
+        out[f'rates0_{i}'] = np.asarray(k_list)
+        out[f'dg0_0_{i}'] = np.asarray(dg0)
+    print(f'{tag}: {total_steps} steps in {dt:.1f} s (reference CPU, doped)')
+    np.savez_compressed(GOLD / f'ref_{tag}.npz', **out)
+
+
+def doped_cases():
+    dope = {'num_dopants': [2, 0], 'min_shell_separation': [1, 1]}
+    doped_case('bvo_doped_init', [2, 0],
+               {'doping': dict(dope, site_charge_initiation=['yes', 'no']), 'random_seed': 3,
+                't_final': 1.0e-4, 'n_traj': 2})
+    doped_case('bvo_doped', [3, 0],
+               {'doping': dict(dope, site_charge_initiation=['no', 'no']), 'random_seed': 4,
+                't_final': 1.0e-4, 'n_traj': 2})
+
+
 def main():
     if not rh.reference_available():
         raise SystemExit('reference not available; golden vectors are already committed')
     TMP.mkdir(exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == 'energy':
         energy_case()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'doped':
+        doped_cases()
         return
     copy_example('Hematite')
     copy_example('BVO')
@@ -176,6 +242,7 @@ def main():
     reference_case('bvo_4e', 'BVO', [4, 0], {'random_seed': 2, 't_final': 3.0e-4, 'n_traj': 1})
     reference_case('bvo_2h', 'BVO', [0, 2], {'random_seed': 5, 't_final': 2.0e-6, 'n_traj': 1})
     energy_case()
+    doped_cases()
 
 
 if __name__ == '__main__':

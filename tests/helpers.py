@@ -38,7 +38,7 @@ def run_parameters(ex, sim=None):
     return RunParameters(ex.lattice, ex.supercell, ex.hop, sim['temp'], sim['ion_charge_type'],
                          sim['species_charge_type'], sim['t_final'], sim['time_interval'],
                          sim['species_count'], sim['initial_occupancy'], sim['relative_energies'],
-                         sim['external_field'])
+                         sim['external_field'], sim.get('doping'))
 
 
 def ewald_parameters(ex):

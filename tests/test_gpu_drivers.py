@@ -136,3 +136,21 @@ def test_energy_and_delg0_outputs(tmp_path):
     dg = np.load(work / 'traj1' / 'delG0_traj.npy')
     assert np.allclose(dg, z['delg0_0'], rtol=1e-9, atol=1e-15)
     assert np.array_equal(dg == 0, z['delg0_0'] == 0)
+
+
+def test_doped_run_consumes_preprod_site_indices(tmp_path):
+    """material_run with dopants: reads each trajectory's site_indices.npy (as written by the
+    reference's material_preprod) and reproduces the reference's doped trajectories."""
+    from pycd_b200 import material_run
+    ex, z = H.load_ref_case('bvo_doped_init')
+    work = _stage('bvo', tmp_path)
+    yaml.safe_dump(yaml.safe_load(str(z['sim_yaml'])), open(work / 'simulation_parameters.yml', 'w'))
+    with pytest.raises(FileNotFoundError, match='site_indices.npy'):
+        material_run(work)
+    for i in range(2):
+        (work / f'traj{i + 1}').mkdir(exist_ok=True)
+        np.save(work / f'traj{i + 1}' / 'site_indices.npy', z[f'site_indices_{i}'])
+    material_run(work)
+    for i in range(2):
+        assert np.array_equal(np.load(work / f'traj{i + 1}' / 'unwrapped_traj.npy'), z[f'unwrapped_{i}'])
+        assert np.allclose(np.load(work / f'traj{i + 1}' / 'time_data.npy'), z[f'time_{i}'], rtol=1e-12, atol=0)

@@ -127,6 +127,81 @@ def test_reference_generated_cases(ctx, tag):
     system.close()
 
 
+@pytest.mark.parametrize('tag', ['bvo_doped_init', 'bvo_doped'])
+def test_doped_reference_cases(ctx, tag):
+    """Doping hooks (core.py:2723-2776) against the reference's own doped runs: per-trajectory
+    site_indices.npy -> shifted site energies, dopant charges, carriers started on dopant sites;
+    both trajectories of the run (different dopant sites) advance in one ensemble."""
+    ex, z = H.load_ref_case(tag)
+    run = H.run_parameters(ex)
+    n_traj = int(z['n_traj'])
+    doping = [run.doping.load(z[f'site_indices_{i}'], run.e_rel, run.q_lat) for i in range(n_traj)]
+    rngs = [H.rng_from_state_bytes(z[f'rnd_state_{i}']) for i in range(n_traj)]
+    occ = np.array([run.initial_occupancy_from(r, d.dopant_site_indices) for r, d in zip(rngs, doping)])
+    for i in range(n_traj):
+        assert list(occ[i]) == list(z[f'occ0_{i}'])
+    system = K.KmcSystem(ctx, run, ex.P)
+    probe = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_REPLAY, doping=doping)
+    probe.advance(1, draws=np.full((n_traj, 2), 0.5))
+    rates = probe.read(unwrapped=False, rates=True)['rates']
+    probe.close()
+    for i in range(n_traj):
+        assert np.allclose(rates[i], z[f'rates0_{i}'], rtol=5e-12, atol=0)
+    state, times, _ = K.run_replay(system, rngs, occ, chunk_steps=8192, want_times=True, doping=doping)
+    for i in range(n_traj):
+        assert int(state['n_steps'][i]) == len(z[f'time_{i}']) - 1
+        assert np.array_equal(state['unwrapped'][i], z[f'unwrapped_{i}'])
+        assert np.allclose(times[i], z[f'time_{i}'], rtol=1e-12, atol=0)
+    system.close()
+
+
+@pytest.mark.parametrize('layout', ['unit_rows', 'dense'])
+@pytest.mark.parametrize('refresh', [1, 16])
+def test_doped_ensemble_matches_oracle_fresh_geometry(ctx, layout, refresh):
+    """Doped Philox ensemble on BVO 3x3x2 (Ewald array from the GPU): every trajectory has its own
+    dopant sites / shifted shells; the checker runs one oracle per trajectory with that
+    trajectory's site energies and lattice charges."""
+    from pycd_b200.doping import TrajectoryDoping
+    from pycd_b200.kmc import RunParameters
+    from pycd_b200.lattice import Supercell
+    ex = H.load_example('bvo')
+    sim = ex.sim
+    sc = Supercell(ex.lattice, [3, 3, 2], [1, 1, 1])
+    run = RunParameters(ex.lattice, sc, sc.hop_neighbor_tables(), sim['temp'], 'full', 'full',
+                        sim['t_final'], sim['time_interval'], [5, 0], {}, sim['relative_energies'],
+                        sim['external_field'])
+    ep = EW.EwaldParameters(sc, ex.cfg['alpha'], ex.cfg['r_cut'], ex.cfg['k_cut'])
+    coords = np.ascontiguousarray(sc.coordinates)
+    p_unit, _ = EW.ewald_rows(ctx, ep, coords, 0, sc.n_per_cell)
+    dense = EW.ewald_expand(ctx, sc, p_unit, 0, sc.num_system_elements)
+    n_traj, steps = 6, 1500
+    rng = np.random.default_rng(5)
+    doping = []
+    for i in range(n_traj):
+        sites = rng.choice(run.tables.sites, size=1 + i % 3, replace=False)   # 1..3 dopants
+        e_rel = run.e_rel.copy()
+        e_rel[sites] += 0.6596 * 0.0367493
+        near = np.unique(run.tables.neigh[run.tables.site_centre[sites]])
+        e_rel[near] += -0.0168 * 0.0367493
+        doping.append(TrajectoryDoping({'W': [int(s) for s in sites]}, e_rel, sites, np.full(len(sites), 1.0)))
+    occ = K.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed=9)
+    kw = dict(dt_grid=run.time_interval / 500, n_path=128, step_limit=steps, stop_at_grid_end=False)
+    system = K.KmcSystem(ctx, run, p_unit if layout == 'unit_rows' else dense, layout=layout)
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=9, refresh_interval=refresh, doping=doping, **kw)
+    while ens.advance_resident(496) > 0:
+        pass
+    got = ens.read()
+    assert ens.last_kernel() == 'kmc_step_kernel'
+    ens.close()
+    system.close()
+    for i in range(n_traj):
+        ref = O.KmcOracle(run, dense, rng_mode=1, seed=9, e_rel=doping[i].e_rel, q_lat=doping[i].q_lat(run.q_lat),
+                          **kw).ensemble(occ[i:i + 1], traj_id0=i)
+        assert got['n_steps'][i] == ref['n_steps'][0]
+        assert np.array_equal(got['occupancy'][i], ref['occupancy'][0])
+        assert np.array_equal(got['unwrapped'][i], ref['unwrapped'][0])
+
+
 def test_vlat_matches_oracle(ctx):
     ex = H.load_example('bvo')
     run = H.run_parameters(ex)

@@ -150,3 +150,32 @@ def test_philox_known_answers():
     assert u[0] == a / 2.0 ** 53
     assert u[1] == (b + 1) / 2.0 ** 53
     assert 0.0 <= u[0] < 1.0 and 0.0 < u[1] <= 1.0
+
+
+@pytest.mark.parametrize('literal', [False, True])
+@pytest.mark.parametrize('tag', ['bvo_doped_init', 'bvo_doped'])
+def test_doped_reference_cases(tag, literal):
+    """Doping hooks of do_kmc_steps (core.py:2723-2776) against the reference's own doped runs:
+    per-trajectory site_indices.npy -> shifted site energies, dopant charges, carriers started on
+    dopant sites (site_charge_initiation)."""
+    ex, z = H.load_ref_case(tag)
+    run = H.run_parameters(ex)
+    assert run.doping.active and not run.doping.pairwise_insertion
+    for i in range(int(z['n_traj'])):
+        dop = run.doping.load(z[f'site_indices_{i}'], run.e_rel, run.q_lat)
+        assert np.array_equal(dop.e_rel, z[f'e_rel_{i}'])
+        rng = H.rng_from_state_bytes(z[f'rnd_state_{i}'])
+        occ = run.initial_occupancy_from(rng, dop.dopant_site_indices)
+        assert list(occ) == list(z[f'occ0_{i}'])
+        q = dop.q_lat(run.q_lat)
+        q_all = q.copy()
+        np.add.at(q_all, occ, run.q_carrier)
+        assert np.array_equal(q_all, z[f'q0_{i}'])
+        n_events = len(z[f'time_{i}']) - 1
+        orc = O.KmcOracle(run, ex.P, literal=literal, e_rel=dop.e_rel, q_lat=q)
+        res = orc.trajectory(occ, H.draw_stream(rng, n_events + 16), want_times=True)
+        assert np.allclose(res['rates0'], z[f'rates0_{i}'], rtol=2e-12, atol=0)
+        assert np.allclose(res['dg0_first'], z[f'dg0_0_{i}'], rtol=0, atol=1e-15)
+        assert res['n_steps'] == n_events
+        assert np.array_equal(res['unwrapped'], z[f'unwrapped_{i}'])
+        assert np.allclose(res['times'], z[f'time_{i}'], rtol=1e-12, atol=0)
