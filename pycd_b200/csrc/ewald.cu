@@ -52,6 +52,15 @@ __global__ void ewald_theta_kernel(const double *__restrict__ coords, long long 
 
 // (cos, sin)(k.r) of one site along a run of the k list: a sincos where a run starts, one
 // complex multiply by e^{i theta_3} where the entry continues the previous one along n3.
+// start of a run of the k list: full-accuracy sincos of n.theta.  Kept out of line: it is taken for
+// ~1 % of the entries and its range reduction would otherwise be inlined into every unrolled step.
+__device__ __noinline__ void phase_restart(double t1, double t2, double t3, int n1, int n2, int n3,
+                                           double *c, double *s)
+{
+    const double arg = fma((double)n1, t1, fma((double)n2, t2, (double)n3 * t3));
+    sincos(arg, s, c);
+}
+
 struct PhaseWalker {
     double t1, t2, t3, c3, s3, c, s;
     __device__ __forceinline__ void init(const double *__restrict__ theta, long long site) {
@@ -63,6 +72,44 @@ struct PhaseWalker {
         if (restart || !(ke.flag & 1)) {
             const double arg = fma((double)ke.n1, t1, fma((double)ke.n2, t2, (double)ke.n3 * t3));
             sincos(arg, &s, &c);
+        } else {
+            const double cn = c * c3 - s * s3;
+            s = fma(s, c3, c * s3);
+            c = cn;
+        }
+    }
+    // same, with the restart out of line (pipelined kernel: the step sits inside the DMMA loop)
+    __device__ __forceinline__ void step_lean(const KEntry ke, bool restart) {
+        if (restart || !(ke.flag & 1)) {
+            double cc, ss;
+            phase_restart(t1, t2, t3, ke.n1, ke.n2, ke.n3, &cc, &ss);
+            c = cc; s = ss;
+        } else {
+            const double cn = c * c3 - s * s3;
+            s = fma(s, c3, c * s3);
+            c = cn;
+        }
+    }
+};
+
+// Walker of the pipelined kernel: only the recurrence state lives in registers; a run start (rare)
+// re-reads the site's theta from global memory and calls the out-of-line sincos.
+struct LeanWalker {
+    double c3, s3, c, s;
+    const double *th;
+    __device__ __forceinline__ void init(const double *__restrict__ theta, long long site) {
+        th = theta + 3 * site;
+        sincos(th[2], &s3, &c3);
+        c = 1.0; s = 0.0;
+    }
+    __device__ __forceinline__ void restart(int n1, int n2, int n3) {
+        double cc, ss;
+        phase_restart(th[0], th[1], th[2], n1, n2, n3, &cc, &ss);
+        c = cc; s = ss;
+    }
+    __device__ __forceinline__ void step_lean(const KEntry ke, bool force) {
+        if (force || !(ke.flag & 1)) {
+            restart(ke.n1, ke.n2, ke.n3);
         } else {
             const double cn = c * c3 - s * s3;
             s = fma(s, c3, c * s3);
@@ -338,6 +385,222 @@ ewald_fourier_dmma_kernel(const double *__restrict__ theta, long long n_sites, l
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Software-pipelined DMMA kernel: the panels are double-buffered and every warp generates the
+// NEXT chunk's panel entries between the DMMA groups of the CURRENT chunk (two k entries per
+// k4 slice), with one block barrier per chunk instead of two.  A chunk without a run start
+// (~7 of 8 at cfg 3) takes a branch-free path -- the phase recurrence only, no k entries, no
+// sincos -- so that the compiler can spread the scalar FP64 chain between the DMMAs; a chunk
+// with a run start takes the generic path.  Skinny tile (32 x 256): thread t owns column t; the
+// 32 row sites are covered by all 8 warps, warp w generating the row entries of k4 slice w (two
+// entries) with a carried phase that jumps 15 entries ahead between chunks (e^{i 15 theta_3}).
+// Measured context (tools/fp64_peak.cu): a 4x4 DMMA tile fed from shared memory reaches 36.9
+// TFLOP/s; every complex-multiply step per 16 DMMAs issued beside it costs ~5 %.
+template <int BM, int BN, int WM, int WN, int KC, int CTAS>
+__global__ void __launch_bounds__(EW_THREADS, CTAS)
+ewald_fourier_pipe_kernel(const double *__restrict__ theta, long long n_sites, long long row0,
+                          long long n_rows, const KEntry *__restrict__ kent,
+                          const double *__restrict__ kw, int n_chunks, int k_split, int n_row_tiles,
+                          int n_col_tiles, double *__restrict__ out)
+{
+    static_assert((BM / WM) * (BN / WN) == EW_THREADS / 32, "8 warps must tile the CTA tile");
+    static_assert(WM % 8 == 0 && WN % 8 == 0 && KC % 2 == 0 && KC <= 32, "m8n8k4 fragments");
+    constexpr int NS = BM + BN;
+    constexpr bool SKINNY = (NS > EW_THREADS);            // BN == 256 columns (one per thread) + 32 rows
+    static_assert(!SKINNY || (BN == EW_THREADS && BM == 32 && KC == 16), "skinny tile: 32 x 256, 16-entry chunks");
+    constexpr int MT = WM / 8, NT = WN / 8, KG = KC / 2;
+    constexpr int PANEL = 2 * KC * NS;                    // doubles per buffer: As [KG][BM][4], then Bs [KG][BN][4]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *panels = reinterpret_cast<double *>(smem_raw);          // [2][PANEL]
+    double *s_w = panels + 2 * PANEL;                                // [2][KC]
+    KEntry *s_ent = reinterpret_cast<KEntry *>(s_w + 2 * KC);        // [2][KC]
+    unsigned *s_mask = reinterpret_cast<unsigned *>(s_ent + 2 * KC); // [2] bit e: entry e starts a run
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int bid = blockIdx.x;
+    const int ct = bid % n_col_tiles; bid /= n_col_tiles;
+    const int rt = bid % n_row_tiles; bid /= n_row_tiles;
+    const int ks = bid;
+    const int c0 = (int)(((long long)ks * n_chunks) / k_split);
+    const int c1 = (int)(((long long)(ks + 1) * n_chunks) / k_split);
+
+    auto row_site = [&](int r) -> long long {
+        const long long s = row0 + (long long)rt * BM + r;
+        return s < n_sites ? s : n_sites - 1;
+    };
+    auto col_site = [&](int c) -> long long {
+        const long long s = (long long)ct * BN + c;
+        return s < n_sites ? s : n_sites - 1;
+    };
+    // primary walker: skinny -> column tid; dense -> tile site tid (rows first, then columns)
+    const bool prim_active = SKINNY || tid < NS;
+    const bool prim_is_row = !SKINNY && tid < BM;
+    const int prim_idx = SKINNY ? tid : (prim_is_row ? tid : tid - BM);
+    LeanWalker pw, rw;
+    pw.init(theta, prim_is_row ? row_site(prim_idx) : col_site(prim_active ? prim_idx : 0));
+    double c15 = 1.0, s15 = 0.0;                          // skinny: e^{i 15 theta_3} of row `lane`
+    if (SKINNY) {
+        rw.init(theta, row_site(lane));
+        sincos(15.0 * rw.th[2], &s15, &c15);
+    }
+
+    // k entries + weights of a chunk travel through registers of warp 0 (loaded one iteration before
+    // they are stored, so that the global-load latency hides under that iteration's DMMAs); the store
+    // also publishes the chunk's run-start mask
+    KEntry e_pre = {0, 0, 0, 0};
+    double w_pre = 0.0;
+    auto fetch_entries = [&](int chunk) {
+        if (tid < KC && chunk < c1) {
+            e_pre = kent[(long long)chunk * KC + tid];
+            w_pre = kw[(long long)chunk * KC + tid];
+        }
+    };
+    auto store_entries = [&](int b) {
+        if (tid < 32) {
+            if (tid < KC) {
+                s_ent[b * KC + tid] = e_pre;
+                s_w[b * KC + tid] = w_pre;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, tid < KC && !(e_pre.flag & 1));
+            if (tid == 0) s_mask[b] = m;
+        }
+    };
+    auto store4 = [](double *dst, double a0, double a1, double a2, double a3) {
+        *reinterpret_cast<double2 *>(dst) = make_double2(a0, a1);
+        *reinterpret_cast<double2 *>(dst + 2) = make_double2(a2, a3);
+    };
+    // generic path: panel entries of k4 slice g (k entries 2g, 2g+1), any run structure
+    auto gen_pair = [&](double *buf, const KEntry *ent, const double *w, int g, bool first) {
+        const KEntry e0 = ent[2 * g], e1 = ent[2 * g + 1];
+        if (prim_active) {
+            pw.step_lean(e0, first);
+            double a0 = pw.c, a1 = pw.s;
+            pw.step_lean(e1, false);
+            double a2 = pw.c, a3 = pw.s;
+            if (prim_is_row) {
+                const double w0 = w[2 * g], w1 = w[2 * g + 1];
+                store4(buf + (g * BM + prim_idx) * 4, a0 * w0, a1 * w0, a2 * w1, a3 * w1);
+            } else {
+                store4(buf + 2 * KC * BM + (g * BN + prim_idx) * 4, a0, a1, a2, a3);
+            }
+        }
+        if (SKINNY && g == wid) {   // this warp's row slice: restart at its first entry
+            const double w0 = w[2 * g], w1 = w[2 * g + 1];
+            rw.step_lean(e0, true);
+            const double a0 = w0 * rw.c, a1 = w0 * rw.s;
+            rw.step_lean(e1, false);
+            store4(buf + (g * BM + lane) * 4, a0, a1, w1 * rw.c, w1 * rw.s);
+            // carried row phase = the chunk's LAST run taken back to this slice's second entry, so that
+            // a following run-continuing chunk finds its entry 2g exactly 15 entries ahead
+            const KEntry el = ent[KC - 1];
+            rw.restart(el.n1, el.n2, el.n3 - (KC - 2 - 2 * g));
+        }
+    };
+    // branch-free path for a chunk that continues every run: phase recurrence only
+    auto gen_pair_fast = [&](double *buf, const double *w, int g) {
+        if (SKINNY || prim_active) {
+            const double a0 = pw.c * pw.c3 - pw.s * pw.s3;
+            const double a1 = fma(pw.s, pw.c3, pw.c * pw.s3);
+            const double a2 = a0 * pw.c3 - a1 * pw.s3;
+            const double a3 = fma(a1, pw.c3, a0 * pw.s3);
+            pw.c = a2; pw.s = a3;
+            if (!SKINNY && prim_is_row) {
+                const double w0 = w[2 * g], w1 = w[2 * g + 1];
+                store4(buf + (g * BM + prim_idx) * 4, a0 * w0, a1 * w0, a2 * w1, a3 * w1);
+            } else {
+                store4(buf + 2 * KC * BM + (g * BN + prim_idx) * 4, a0, a1, a2, a3);
+            }
+        }
+        if (SKINNY && g == wid) {   // rows: 15 entries ahead of the previous chunk's last one, then one more
+            const double w0 = w[2 * g], w1 = w[2 * g + 1];
+            const double a0 = rw.c * c15 - rw.s * s15;
+            const double a1 = fma(rw.s, c15, rw.c * s15);
+            const double a2 = a0 * rw.c3 - a1 * rw.s3;
+            const double a3 = fma(a1, rw.c3, a0 * rw.s3);
+            rw.c = a2; rw.s = a3;
+            store4(buf + (g * BM + lane) * 4, a0 * w0, a1 * w0, a2 * w1, a3 * w1);
+        }
+    };
+
+    const int m0 = (wid % (BM / WM)) * WM, n0 = (wid / (BM / WM)) * WN;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // prologue: k entries of the first two chunks, panel of the first (generic path, forced start)
+    fetch_entries(c0);
+    store_entries(0);
+    fetch_entries(c0 + 1);
+    store_entries(1);
+    fetch_entries(c0 + 2);
+    __syncthreads();
+    if (c0 < c1) {
+#pragma unroll
+        for (int g = 0; g < KG; ++g) gen_pair(panels, s_ent, s_w, g, g == 0);
+    }
+    __syncthreads();
+
+    for (int chunk = c0; chunk < c1; ++chunk) {
+        const int cur = (chunk - c0) & 1, nxt = cur ^ 1;
+        const bool has_next = chunk + 1 < c1;
+        const bool fast = has_next && s_mask[nxt] == 0u;
+        // k entries of chunk + 2 (in registers since the previous iteration) replace those of `chunk`,
+        // consumed one iteration ago and read again only after this iteration's barrier
+        if (chunk + 2 < c1) store_entries(cur);
+        fetch_entries(chunk + 3);
+        const double *Aw = panels + cur * PANEL + (size_t)m0 * 4 + lane;
+        const double *Bw = panels + cur * PANEL + 2 * KC * BM + (size_t)n0 * 4 + lane;
+        double *nbuf = panels + nxt * PANEL;
+        const KEntry *nent = s_ent + nxt * KC;
+        const double *nw = s_w + nxt * KC;
+        if (fast) {
+#pragma unroll
+            for (int g = 0; g < KG; ++g) {
+                double a[MT], b[NT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) a[i] = Aw[(g * BM + i * 8) * 4];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) b[j] = Bw[(g * BN + j * 8) * 4];
+                gen_pair_fast(nbuf, nw, g);
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        } else {
+#pragma unroll 1
+            for (int g = 0; g < KG; ++g) {
+                double a[MT], b[NT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) a[i] = Aw[(g * BM + i * 8) * 4];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) b[j] = Bw[(g * BN + j * 8) * 4];
+                if (has_next) gen_pair(nbuf, nent, nw, g, false);
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        __syncthreads();   // next panel complete; this panel and the next chunk's k entries consumed
+    }
+
+    double *o = out + (long long)ks * n_rows * n_sites;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const long long row = (long long)rt * BM + m0 + i * 8 + (lane >> 2);
+        if (row >= n_rows) continue;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const long long col = (long long)ct * BN + n0 + j * 8 + (lane & 3) * 2;
+            if (col < n_sites) o[row * n_sites + col] = acc[i][j][0];
+            if (col + 1 < n_sites) o[row * n_sites + col + 1] = acc[i][j][1];
+        }
+    }
+}
+
 struct FinishParams {
     double cell[9], cellinv[9];
     int pbc[3];
@@ -491,6 +754,21 @@ static void launch_fourier_dmma(pycd_ctx *ctx, const double *theta, long long n,
     check_launch(ctx, "ewald_fourier_dmma_kernel");
 }
 
+template <int BM, int BN, int WM, int WN, int KC, int CTAS>
+static void launch_fourier_pipe(pycd_ctx *ctx, const double *theta, long long n, long long row0,
+                                long long n_rows, const KEntry *kent, const double *kw, int n_chunks,
+                                int k_split, double *out) {
+    auto kern = ewald_fourier_pipe_kernel<BM, BN, WM, WN, KC, CTAS>;
+    const size_t smem = 2 * (sizeof(double) * (size_t)(2 * KC) * (BM + BN) + (sizeof(KEntry) + sizeof(double)) * KC) + 16;
+    PYCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_row_tiles = (int)((n_rows + BM - 1) / BM), n_col_tiles = (int)((n + BN - 1) / BN);
+    const long long grid = (long long)k_split * n_row_tiles * n_col_tiles;
+    PYCD_REQUIRE(grid < (1ll << 31), "grid too large");
+    kern<<<(unsigned)grid, EW_THREADS, smem, ctx->stream>>>(
+        theta, n, row0, n_rows, kent, kw, n_chunks, k_split, n_row_tiles, n_col_tiles, out);
+    check_launch(ctx, "ewald_fourier_pipe_kernel");
+}
+
 }  // namespace pycd
 
 using namespace pycd;
@@ -504,14 +782,20 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         PYCD_REQUIRE(desc->alpha > 0 && desc->volume > 0 && desc->dielectric > 0, "bad Ewald parameters");
         DeviceGuard g(ctx);
         const long long n_rows = row_end - row_begin;
-        // wide tile (128x128, 32-entry chunks, 1 CTA/SM) for big row blocks, skinny tile
-        // (32x256, 16-entry chunks, 2 CTAs/SM) for the rows of one unit cell
+        // dense tile (64x128) for big row blocks, skinny tile (32x256) for the rows of one unit cell
         const bool wide = n_rows > 64;
-        // kernel variant: "dmma" (default: DMMA accumulation, 2 CTAs/SM) or "dfma" (register-tiled
-        // DFMA; kept for A/B measurements, PYCD_EWALD_VARIANT=dfma)
+        // kernel variant (PYCD_EWALD_VARIANT, for A/B measurements): default = software-pipelined DMMA
+        // kernel with 16-entry chunks (dense tile 64x128: 2 CTAs/SM; skinny tile 32x256: 1 CTA/SM with
+        // 147 KB of double-buffered panels); "pipe16x1" / "pipe8" / "pipe8x1" = other chunk sizes / CTAs
+        // per SM of it (dense tile only); "phased" = two-phase DMMA kernel; "dfma" = register-tiled DFMA
         const char *var_env = getenv("PYCD_EWALD_VARIANT");
-        const bool use_dmma = !(var_env && std::string(var_env) == "dfma");
-        const int KC = (wide && !use_dmma) ? 32 : 16;
+        const std::string variant = var_env ? var_env : "";
+        const bool use_dmma = variant != "dfma";
+        const bool phased = variant == "phased";
+        const bool pipe8 = variant == "pipe8" || variant == "pipe8x1";
+        const bool pipe16 = use_dmma && !phased && !pipe8;
+        const bool one_cta = variant == "pipe16x1" || variant == "pipe8x1";
+        const int KC = (wide && !use_dmma) ? 32 : 16;   // the k list is padded to a multiple of KC
 
         std::vector<KEntry> ent;
         std::vector<double> w;
@@ -544,7 +828,7 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
             // candidates pick the best-filled last wave, preferring fewer splits on ties
             const long long ws_cap = std::max(1ll, (1ll << 30) / (n_rows * n * 8));
             const long long ks_max = std::min({(long long)n_chunks, ws_cap, 32ll});
-            const long long slots = (long long)ctx->n_sm * ((use_dmma || !wide) ? 2 : 1);
+            const long long slots = (long long)ctx->n_sm * ((one_cta || ((pipe16 || pipe8) && !wide)) ? 1 : (use_dmma || !wide) ? 2 : 1);
             double best_fill = -1.0;
             for (long long ks = 1; ks <= ks_max; ++ks) {
                 const long long grid = tiles * ks;
@@ -561,7 +845,22 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         }
         KernelTimer tf(ctx, KC_EWALD_FOURIER);
         if (n_chunks > 0) {
-            if (use_dmma && wide)
+            if (pipe16 && wide && one_cta)
+                launch_fourier_pipe<64, 128, 32, 32, 16, 1>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                            n_chunks, k_split, partials);
+            else if (pipe8 && wide && one_cta)
+                launch_fourier_pipe<64, 128, 32, 32, 8, 1>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                           2 * n_chunks, k_split, partials);
+            else if (pipe16 && wide)
+                launch_fourier_pipe<64, 128, 32, 32, 16, 2>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                            n_chunks, k_split, partials);
+            else if ((pipe16 || pipe8) && !wide)
+                launch_fourier_pipe<32, 256, 32, 32, 16, 1>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                            n_chunks, k_split, partials);
+            else if (pipe8 && wide)
+                launch_fourier_pipe<64, 128, 32, 32, 8, 2>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
+                                                           2 * n_chunks, k_split, partials);
+            else if (use_dmma && wide)
                 launch_fourier_dmma<64, 128, 32, 32, 16>(ctx, theta.p, n, row_begin, n_rows, kent.p, kw.p,
                                                          n_chunks, k_split, partials);
             else if (use_dmma)

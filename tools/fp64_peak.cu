@@ -69,6 +69,101 @@ __global__ void dmma_kernel(double *out, int iters, double seed)
     if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// ---- what the Ewald kernel actually issues: 4x4 accumulator tiles with distinct fragments, fragments
+// from shared memory, and scalar FP64 work (the phase recurrence) sharing the pipe ----
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// MODE 0: 4x4 tile, fragments in registers.  MODE 1: fragments re-read from shared memory every k4 slice
+// (8 LDS.64 per 16 DMMA, the kernel's ratio).  NF: dependent scalar-FP64 complex-multiply steps
+// (2 DMUL + 2 DFMA each) issued by the same warp per 16 DMMAs.
+template <int MODE, int NF>
+__global__ void dmma_tile_kernel(double *out, int iters, double seed)
+{
+    __shared__ double frag[2][8][32];
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int lane = threadIdx.x & 31;
+    for (int i = 0; i < 8; ++i) { frag[0][i][lane] = seed + i + lane * 1e-3; frag[1][i][lane] = seed * 0.5 + i; }
+    __syncthreads();
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = frag[0][i][lane]; b[i] = frag[0][4 + i][lane]; }
+    double c = 1.0, s = 0.0;
+    const double c3 = 0.9999995, s3 = 0.001;
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 1) {
+            const volatile double *f = &frag[it & 1][0][0];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = f[i * 32 + lane]; b[i] = f[(4 + i) * 32 + lane]; }
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            const double cn = c * c3 - s * s3;
+            s = fma(s, c3, c * s3);
+            c = cn;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    double t = c + s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t += acc[i][j][0] + acc[i][j][1];
+    if (t == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
+// warp-specialised mix: warps [0, NGEN) run NCH independent dependent complex-multiply chains,
+// the other warps the 4x4 DMMA tile; both loop `iters` times (the DMMA warps do 16 DMMA per
+// iteration, the scalar warps NSTEP chain steps per iteration).
+template <int NGEN, int NSTEP>
+__global__ void dmma_split_kernel(double *out, int iters, double seed)
+{
+    const int wid = threadIdx.x >> 5;
+    if (wid < NGEN) {
+        double c = 1.0 + threadIdx.x * 1e-9, s = 0.0;
+        const double c3 = 0.9999995, s3 = 0.001;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int q = 0; q < NSTEP; ++q) {
+                const double cn = c * c3 - s * s3;
+                s = fma(s, c3, c * s3);
+                c = cn;
+            }
+        }
+        if (c + s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = c;
+        return;
+    }
+    double acc[4][4][2], a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] = seed + i + threadIdx.x * 1e-9; b[i] = seed * 0.5 + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    double t = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t += acc[i][j][0] + acc[i][j][1];
+    if (t == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
 template <typename F>
 static double time_ms(F launch)
 {
@@ -125,6 +220,26 @@ int main()
                 rep("dmma_m8n8k4_x16", 2.0 * 256 * 16 * (iters / 4) * (double)(t / 32) * grid, ms);
             }
         }
+    }
+
+    // DMMA flops only (the scalar work is overhead, as in the Ewald kernel)
+    for (int bps = 1; bps <= 2; ++bps) {
+        const int t = 256, grid = sms * bps, it2 = iters / 4;
+        auto rep2 = [&](const char *name, double warps, double ms) {
+            printf(",\n{\"kernel\": \"%s\", \"threads\": %d, \"ctas_per_sm\": %d, \"dmma_tflops\": %.2f}", name, t, bps,
+                   2.0 * 256 * 16 * it2 * warps * grid / (ms * 1e-3) / 1e12);
+        };
+        double ms;
+        ms = time_ms([&] { dmma_tile_kernel<0, 0><<<grid, t>>>(out, it2, 1.5); }); rep2("tile4x4_regs", 8, ms);
+        ms = time_ms([&] { dmma_tile_kernel<1, 0><<<grid, t>>>(out, it2, 1.5); }); rep2("tile4x4_lds", 8, ms);
+        ms = time_ms([&] { dmma_tile_kernel<0, 1><<<grid, t>>>(out, it2, 1.5); }); rep2("tile4x4_regs+1cmul/16", 8, ms);
+        ms = time_ms([&] { dmma_tile_kernel<0, 2><<<grid, t>>>(out, it2, 1.5); }); rep2("tile4x4_regs+2cmul/16", 8, ms);
+        ms = time_ms([&] { dmma_tile_kernel<0, 4><<<grid, t>>>(out, it2, 1.5); }); rep2("tile4x4_regs+4cmul/16", 8, ms);
+        ms = time_ms([&] { dmma_tile_kernel<1, 2><<<grid, t>>>(out, it2, 1.5); }); rep2("tile4x4_lds+2cmul/16", 8, ms);
+        ms = time_ms([&] { dmma_split_kernel<1, 4><<<grid, t>>>(out, it2, 1.5); }); rep2("split_7dmma+1gen(4 steps)", 7, ms);
+        ms = time_ms([&] { dmma_split_kernel<1, 16><<<grid, t>>>(out, it2, 1.5); }); rep2("split_7dmma+1gen(16 steps)", 7, ms);
+        ms = time_ms([&] { dmma_split_kernel<2, 8><<<grid, t>>>(out, it2, 1.5); }); rep2("split_6dmma+2gen(8 steps)", 6, ms);
+        ms = time_ms([&] { dmma_split_kernel<4, 4><<<grid, t>>>(out, it2, 1.5); }); rep2("split_4dmma+4gen(4 steps)", 4, ms);
     }
     printf("\n]}\n");
     return 0;
