@@ -19,7 +19,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'TPC.TriageCompute.sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
         'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
-        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum']
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
+        'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed']
 
 
 def ncu_csv(rep, page):
