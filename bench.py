@@ -195,6 +195,27 @@ def cpu_reference_rate(run, P_host, occ, args, n_traj, steps_per_traj, n_path, d
     return res['total_steps'] / dt, dt, res['total_steps'], threads
 
 
+def ewald_cpu_baseline(sc, ep, n_sample=64):
+    """The literal Ewald evaluation of the reference (core.py:799-878: one cos per (pair, k) term, all
+    K_eff half-space vectors) timed by the oracle on n_sample sites of the bench supercell with all host
+    threads, and extrapolated to the N x N array (cost is proportional to N^2 K_eff)."""
+    import oracle as O
+    n = sc.num_system_elements
+    sites = np.random.default_rng(7).choice(n, size=n_sample, replace=False)
+    pair = O.pairwise(np.ascontiguousarray(sc.coordinates[sites]), sc.cell_matrix, sc.cell_matrix_inv, sc.pbc)
+    t0 = time.perf_counter()
+    _, keff = O.ewald_literal(pair, sc.reciprocal_lattice_matrix, sc.system_volume, ep.alpha, ep.r_cut,
+                              ep.k_cut, ep.dielectric, ep.k_max)
+    dt = time.perf_counter() - t0
+    ns_term = dt / (n_sample * n_sample * keff) * 1e9
+    return {'kind': 'port', 'cores': host_cores(),
+            'sample': f'{n_sample} x {n_sample} site pairs x {keff} k-vectors, literal cos sum (oracle), {dt:.1f} s',
+            'ns_per_pair_k_term': ns_term,
+            'seconds_full_array_extrapolated': ns_term * 1e-9 * n * n * keff,
+            'note': 'extrapolated in proportion to N^2 K_eff; the reference itself (numpy temporaries, one '
+                    'core) measures 20.4 ns per term (SURVEY 8a)'}
+
+
 def size_cpu_sample(run, P_host, occ, args, n_path, dt_grid, seed, literal):
     """Pick (#trajectories, steps) so that the sample costs about args.cpu_seconds."""
     cores = host_cores()
@@ -420,6 +441,7 @@ def main():
                'gather_form_value': rate_g,
                'gather_form_sample': f'{n_g} trajectories x {steps_g} steps, O(C) gather restatement, {dt_g:.1f} s'}
         del P_host
+        ewald_info['cpu_baseline'] = ewald_cpu_baseline(sc, ep)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
