@@ -1743,6 +1743,20 @@ static void launch_step(pycd_ctx *ctx, bool compact, const SysDev &S, const EnsD
     else launch_step_impl<BS, false, 0, 0>(ctx, S, E, A, smem);
 }
 
+// kmc_step_warp_kernel is compiled per mode: INCR (refresh_interval > 1) and PLAIN (no field, no energy
+// outputs, no per-step event / time outputs), so that the production shape carries none of those tests
+template <int NWC, int CPL, int NN>
+static void launch_warp_step(pycd_ctx *ctx, unsigned grid, size_t smem, const SysDev &S, const StencilDev &T,
+                             const EnsDev &E, const AdvanceArgs &A) {
+    const bool incr = E.refresh_interval > 1;
+    const bool plain = !E.energy && !S.field_active && !E.field_traj && !A.events_out && !A.times_out;
+    const unsigned bs = 32 * NWC;
+    if (incr && plain) kmc_step_warp_kernel<NWC, CPL, NN, true, true><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
+    else if (incr) kmc_step_warp_kernel<NWC, CPL, NN, true, false><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
+    else if (plain) kmc_step_warp_kernel<NWC, CPL, NN, false, true><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
+    else kmc_step_warp_kernel<NWC, CPL, NN, false, false><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
+}
+
 extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
                                 int32_t *events_out, double *times_out, int64_t *steps_done,
                                 int64_t *n_active) {
@@ -1801,9 +1815,9 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
             // (finished trajectories leave their CTA at once, so the ACTIVE count decides)
             const long long live = ens->n_active >= 0 ? ens->n_active : (long long)E.n_traj;
             const bool wide = E.C > 32 && live <= 4ll * ctx->n_sm && variant != "stencil_1warp";
-            if (E.C <= 32) kmc_step_warp_kernel<1, 1, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            else if (wide) kmc_step_warp_kernel<2, 1, 4><<<g, 64, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
-            else kmc_step_warp_kernel<1, 2, 4><<<g, 32, sm, ctx->stream>>>(ens->sys->dev, ens->sys->st, E, A);
+            if (E.C <= 32) launch_warp_step<1, 1, 4>(ctx, g, sm, ens->sys->dev, ens->sys->st, E, A);
+            else if (wide) launch_warp_step<2, 1, 4>(ctx, g, sm, ens->sys->dev, ens->sys->st, E, A);
+            else launch_warp_step<1, 2, 4>(ctx, g, sm, ens->sys->dev, ens->sys->st, E, A);
             const int nwc = wide ? 2 : 1, cpl = (E.C <= 32 || wide) ? 1 : 2;
             check_launch(ctx, "kmc_step_warp_kernel");
             ens->last_kernel = "kmc_step_warp_kernel<" + std::to_string(nwc) + "," + std::to_string(cpl) + ",4>";
