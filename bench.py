@@ -195,7 +195,7 @@ def cpu_reference_rate(run, P_host, occ, args, n_traj, steps_per_traj, n_path, d
     return res['total_steps'] / dt, dt, res['total_steps'], threads
 
 
-def ewald_cpu_baseline(sc, ep, n_sample=64):
+def ewald_cpu_baseline(sc, ep, n_sample=32):
     """The literal Ewald evaluation of the reference (core.py:799-878: one cos per (pair, k) term, all
     K_eff half-space vectors) timed by the oracle on n_sample sites of the bench supercell with all host
     threads, and extrapolated to the N x N array (cost is proportional to N^2 K_eff)."""
