@@ -265,3 +265,25 @@ def test_product_never_imports_the_oracle():
         if f.suffix in ('.py', '.cu', '.cuh', '.h'):
             src = f.read_text()
             assert 'oracle' not in src and 'ref_harness' not in src, f
+
+
+def test_bench_cpu_legs_run_without_a_gpu():
+    """bench.py's host-side pieces: the algorithmic-bytes formula of SURVEY 8(d), the Ewald CPU baseline
+    (literal oracle on a sample of site pairs, extrapolated) and the reference arm's small fallback."""
+    import json
+    import subprocess
+    from types import SimpleNamespace
+    import bench
+    assert bench.b_step_bytes(256, 64) == 275456          # cfg 3: 8*n_proc*(2C+6) + 4*n_proc
+    assert bench.b_step_bytes(4, 1) == 272                # cfg 1
+    lat, sc, run, ep = bench.build_problem(SimpleNamespace(size=[2, 2, 1], carriers=4))
+    base = bench.ewald_cpu_baseline(sc, ep, n_sample=8)
+    assert base['kind'] == 'port' and base['ns_per_pair_k_term'] > 0
+    n = sc.num_system_elements
+    assert np.isclose(base['seconds_full_array_extrapolated'],
+                      base['ns_per_pair_k_term'] * 1e-9 * n * n * 3457, rtol=1e-12)
+    out = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0', '--cpu-seconds', '0.5'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
