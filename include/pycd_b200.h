@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PYCD_ABI_VERSION 2
+#define PYCD_ABI_VERSION 3
 
 typedef struct pycd_ctx pycd_ctx;
 typedef struct pycd_kmc_system pycd_kmc_system;
@@ -60,6 +60,12 @@ int pycd_ctx_flush_l2(pycd_ctx *ctx);
  * H2D/D2H copies of a call run at PCIe speed instead of through pageable staging). */
 int pycd_host_alloc(int64_t bytes, void **out);
 int pycd_host_free(void *ptr);
+
+/* NVTX ranges (SURVEY section 5 tracing hook).  Every compute entry point below opens its own range
+ * ("pycd.ewald_rows", "pycd.ewald_expand", "pycd.kmc_system_create", "pycd.kmc_advance", "pycd.msd");
+ * the drivers bracket their phases (material_setup / material_run / material_msd) with these two. */
+int pycd_nvtx_push(const char *name);
+int pycd_nvtx_pop(void);
 
 /* ---- Ewald site-pair array --------------------------------------------- */
 /* Replaces System.pot_r_ewald / pot_k_ewald / get_precomputed_array
@@ -184,8 +190,9 @@ int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *occupancy0, u
  * (core.py:1989-2050), selection + time advance + recording (core.py:2796-2861).
  * draws: REPLAY mode, (n_traj, 2*max_steps) u1,u2,...; ignored for PHILOX.
  * events_out / times_out: NULL or (n_traj, max_steps): selected process index and
- * simulation time after each step of this call (entries past a trajectory's end are
- * left untouched).  steps_done: NULL or (n_traj) steps taken in this call.
+ * simulation time after each step of this call; entries past a trajectory's end hold -1 / 0.0
+ * in HOST buffers and are left untouched in DEVICE buffers.  steps_done: NULL or (n_traj) steps
+ * taken in this call.
  * n_active: number of trajectories still unfinished after the call. */
 int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
                      int32_t *events_out, double *times_out, int64_t *steps_done,
@@ -197,6 +204,15 @@ int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *dr
 int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t *n_steps, double *sim_time,
                   int32_t *occupancy, double *drift, int64_t *near_tie, int64_t *clamped,
                   double *rates /* (n_traj, C*nn) rates of the last evaluated step */);
+/* Pipelined read-back for batch production (HOST buffers, ideally page-locked; any may be NULL):
+ * pycd_kmc_read_begin snapshots the state reached by the launches issued so far and copies it out on
+ * a second stream while the caller re-arms the ensemble (pycd_kmc_ensemble_reset, REQUIRED before the
+ * next pycd_kmc_advance when `unwrapped` was requested: the ensemble switches to its second displacement
+ * grid) and runs the next batch.  pycd_kmc_read_end blocks until the buffers are complete.  One read in
+ * flight per ensemble; not available with energy outputs. */
+int pycd_kmc_read_begin(pycd_kmc_ensemble *ens, double *unwrapped, int64_t *n_steps, double *sim_time,
+                        int32_t *occupancy, double *drift, int64_t *near_tie, int64_t *clamped);
+int pycd_kmc_read_end(pycd_kmc_ensemble *ens);
 /* output_data 'energy' and 'delg_0' (core.py:2807-2809, 2855-2857): (n_traj, n_path) each; either may be NULL */
 int pycd_kmc_read_energy(pycd_kmc_ensemble *ens, double *energy_grid, double *dg0_grid);
 /* device pointer of the resident displacement grid (input of pycd_msd without a copy) */

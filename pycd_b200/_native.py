@@ -15,9 +15,12 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PKG_DIR / 'csrc'
 LIB_PATH = PKG_DIR / 'libpycd_b200.so'
-SOURCES = ['ctx.cu', 'ewald.cu', 'kmc.cu', 'msd.cu']
+SOURCES = ['ctx.cu', 'ewald.cu', 'kmc.cu', 'kmc_stencil_nn4.cu', 'kmc_stencil_nn8.cu', 'kmc_stencil_nn12.cu',
+           'msd.cu']
+HEADERS = ['common.cuh', 'kmc_types.cuh', 'kmc_stencil.cuh', 'kmc_stencil_launch.h']
+OBJ_DIR = CSRC_DIR / 'build'
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC']
 
 KC_EWALD_FOURIER, KC_EWALD_FINISH, KC_EWALD_EXPAND, KC_KMC_STEP, KC_MSD, KC_VLAT = range(6)
 RNG_REPLAY, RNG_PHILOX = 0, 1
@@ -39,27 +42,46 @@ def needs_build():
     if not LIB_PATH.exists():
         return True
     t = LIB_PATH.stat().st_mtime
-    deps = [CSRC_DIR / s for s in SOURCES] + [CSRC_DIR / 'common.cuh', CSRC_DIR / 'kmc_stencil.cuh',
-                                              PKG_DIR.parent / 'include' / 'pycd_b200.h']
+    deps = [CSRC_DIR / s for s in SOURCES + HEADERS] + [PKG_DIR.parent / 'include' / 'pycd_b200.h']
     return any(d.stat().st_mtime > t for d in deps if d.exists())
 
 
-def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> pycd_b200/libpycd_b200.so"""
-    if not force and not needs_build():
+def build(force=False, verbose=False, lib_path=None, extra=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> pycd_b200/libpycd_b200.so.
+    The translation units compile in parallel (one nvcc -c each), then link.  lib_path / extra build a
+    variant library beside the default one (A/B measurements: tools/)."""
+    lib_path = Path(lib_path) if lib_path else LIB_PATH
+    if not force and lib_path == LIB_PATH and not needs_build():
         return LIB_PATH
-    extra = os.environ.get('PYCD_NVCC_EXTRA', '').split()   # e.g. -DPYCD_TRACE (tools/step_trace.py)
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-o', str(LIB_PATH)] + [str(CSRC_DIR / s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    extra = list(extra) if extra is not None else os.environ.get('PYCD_NVCC_EXTRA', '').split()  # e.g. -DPYCD_TRACE
     env = dict(os.environ)
     env.pop('CC', None)   # the image exports a gcc wrapper that nvcc must not pick up
     env.pop('CXX', None)
+    obj_dir = OBJ_DIR / lib_path.stem
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = obj_dir / (Path(src).stem + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
+              ['-c', '-o', str(obj), str(CSRC_DIR / src)]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise NativeError(f'nvcc failed on {src}:\n' + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    if verbose:
+        for _, err in results:
+            print(err)
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', str(lib_path)] + \
+          [str(o) for o, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if res.returncode != 0:
-        raise NativeError('nvcc failed:\n' + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    return LIB_PATH
+        raise NativeError('nvcc link failed:\n' + res.stdout + res.stderr)
+    return lib_path
 
 
 class EwaldDesc(C.Structure):
@@ -130,6 +152,10 @@ _SIGNATURES = {
     'pycd_kmc_read_energy': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pycd_kmc_unwrapped_device': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'pycd_kmc_last_kernel': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    'pycd_nvtx_push': (C.c_int, [C.c_char_p]),
+    'pycd_nvtx_pop': (C.c_int, []),
+    'pycd_kmc_read_begin': (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),
+    'pycd_kmc_read_end': (C.c_int, [C.c_void_p]),
     'pycd_kmc_system_stencil': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_char_p,
                                           C.c_int32]),
     'pycd_msd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
@@ -144,10 +170,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise NativeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; '
+    path = Path(os.environ.get('PYCD_B200_LIB') or LIB_PATH)   # PYCD_B200_LIB: a variant build (A/B measurements)
+    if not path.exists():
+        raise NativeError(f'{path} is missing: run `python -c "import __graft_entry__ as g; '
                           f'g.build()"` (there is no CPU fallback)')
-    handle = C.CDLL(str(LIB_PATH))
+    handle = C.CDLL(str(path))
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(handle, name)
         fn.restype = restype
@@ -235,6 +262,22 @@ class Context:
 
     def flush_l2(self):
         check(lib().pycd_ctx_flush_l2(self.handle))
+
+
+class nvtx_range:
+    """NVTX range around a phase of the host driver (Ewald / step batches / MSD), visible to nsys / ncu
+    --nvtx.  Pushed through the library (nvtx3 is header-only inside libpycd_b200.so)."""
+
+    def __init__(self, name):
+        self.name = name.encode()
+
+    def __enter__(self):
+        lib().pycd_nvtx_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        lib().pycd_nvtx_pop()
+        return False
 
 
 _default_ctx = {}

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -49,6 +50,7 @@ struct pycd_ctx {
     int64_t class_launches[pycd::KC_COUNT] = {0, 0, 0, 0, 0, 0};
     void *flush_buf = nullptr;
     int flush_value = 0;
+    cudaStream_t copy_stream = nullptr;   // pipelined read-back (pycd_kmc_read_begin / _end)
 };
 
 namespace pycd {
@@ -151,6 +153,14 @@ struct KernelTimer {
         ctx->total_ms[cls] += ms;
         ctx->class_launches[cls] += n_launch;
     }
+};
+
+// NVTX range around a library call (visible to nsys / ncu --nvtx; a no-op without a tool attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
 inline void check_launch(pycd_ctx *ctx, const char *name) {

@@ -55,6 +55,7 @@ int pycd_ctx_create(int device, pycd_ctx **out) {
         ctx->n_sm = prop.multiProcessorCount;
         PYCD_CUDA(cudaSetDevice(device));
         PYCD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        PYCD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int k = 0; k < KC_COUNT; ++k)
             for (int j = 0; j < 2; ++j) PYCD_CUDA(cudaEventCreate(&ctx->ev[k][j]));
         *out = ctx;
@@ -70,6 +71,8 @@ int pycd_ctx_destroy(pycd_ctx *ctx) {
             for (int j = 0; j < 2; ++j)
                 if (ctx->ev[k][j]) cudaEventDestroy(ctx->ev[k][j]);
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
         cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -124,6 +127,16 @@ int pycd_host_free(void *ptr) {
     return guarded([&] {
         if (ptr) PYCD_CUDA(cudaFreeHost(ptr));
     });
+}
+
+int pycd_nvtx_push(const char *name) {
+    nvtxRangePushA(name ? name : "pycd");
+    return 0;
+}
+
+int pycd_nvtx_pop(void) {
+    nvtxRangePop();
+    return 0;
 }
 
 int pycd_ctx_reset_timers(pycd_ctx *ctx) {

@@ -776,6 +776,7 @@ using namespace pycd;
 extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64_t row_begin,
                                int64_t row_end, double *out, pycd_ewald_stats *stats) {
     return guarded([&] {
+        NvtxRange nvtx("pycd.ewald_rows");
         PYCD_REQUIRE(ctx && desc && out, "NULL argument");
         const long long n = desc->n_sites;
         PYCD_REQUIRE(n > 0 && row_begin >= 0 && row_end <= n && row_begin < row_end, "bad row range");
@@ -911,6 +912,7 @@ extern "C" int pycd_ewald_expand(pycd_ctx *ctx, const double *p_unit, int32_t n_
                                  const int32_t size[3], int64_t row_begin, int64_t row_end,
                                  double *out) {
     return guarded([&] {
+        NvtxRange nvtx("pycd.ewald_expand");
         PYCD_REQUIRE(ctx && p_unit && size && out, "NULL argument");
         PYCD_REQUIRE(n_basis > 0 && size[0] > 0 && size[1] > 0 && size[2] > 0, "bad supercell");
         const long long n = (long long)n_basis * size[0] * size[1] * size[2];

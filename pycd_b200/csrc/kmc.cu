@@ -8,7 +8,7 @@
 // refresh_interval = 1 re-gathers every process every step (the stateless
 // formulation the roofline figure B_step counts); R > 1 patches the cached sums
 // after each hop (4 gathers per untouched process) and re-gathers every R steps.
-#include "common.cuh"
+#include "kmc_types.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -17,94 +17,6 @@
 
 namespace pycd {
 
-struct SysDev {
-    const double *P;          // dense: [N][N]; compact: [n_basis][N] (rows of unit cell 0)
-    long long n_sites;
-    const int *site_centre;
-    const int *site_class;
-    const unsigned *site_pack;  // compact only: basis | x<<8 | y<<16 | z<<24
-    int nn;
-    const int *neigh;
-    const unsigned *neigh_pack; // compact only: site_pack of neigh[e][slot]
-    const int *neigh2;          // [n_centres][nn][nn]: neighbours of the neighbours (carrier kernel)
-    const unsigned *neigh2_pack;
-    const double *hopvec;
-    const double *lam;
-    const double *vab;
-    const double *i4l;        // 1/(4 lambda) per (class, slot)
-    const double *e_rel;
-    const double *v_lat;      // dense: [N]; compact: [n_basis] (doped trajectory: [N] either way)
-    int vlat_by_site;         // 1: v_lat is indexed by site in the compact layout too (doped trajectory)
-    double qc, kT, vn;
-    double field[3];
-    int field_active;
-    int n_basis, sx, sy, sz;  // compact only
-};
-
-struct EnsDev {
-    int C, n_proc;
-    long long n_traj;
-    unsigned long long traj_id0;
-    int *occ;              // [n_traj][C]
-    double *t;             // [n_traj]
-    long long *start_idx;  // [n_traj]
-    int *done;             // [n_traj]
-    double *disp;          // [n_traj][3C] hops since the last recorded row
-    double *row;           // [n_traj][3C] last recorded row
-    long long *n_steps;    // [n_traj]
-    long long *near_tie;   // [n_traj]
-    long long *clamped;    // [n_traj]
-    double *drift;         // [n_traj][3C]
-    double *rates;         // [n_traj][n_proc]
-    const double *kT_traj;
-    const double *field_traj;
-    const double *e_rel_traj;  // NULL or [n_traj][N]: a doped trajectory's site energies (core.py:2750-2764)
-    const double *v_lat_traj;  // NULL or [n_traj][N]: its lattice potential, dopant charges included
-    double *unwrapped;     // [n_traj][n_path][3C] or NULL
-    double *energy;        // [n_traj] current_state_energy, or NULL (energy outputs off)
-    double *energy_grid;   // [n_traj][n_path]
-    double *dg0_grid;      // [n_traj][n_path]
-    double dt_grid;
-    long long n_path;
-    long long step_limit;
-    int stop_at_grid_end;
-    int rng_mode;
-    unsigned long long seed;
-    int refresh_interval;
-};
-
-struct AdvanceArgs {
-    long long max_steps;
-    const double *draws;   // [n_traj][2*max_steps]
-    int *events_out;       // [n_traj][max_steps]
-    double *times_out;     // [n_traj][max_steps]
-    long long *steps_done; // [n_traj]
-};
-
-// Philox4x32-10; identical to the CPU checker's generator (tests pin both to the
-// Random123 known-answer vector)
-__device__ __forceinline__ void philox_uniforms(unsigned long long seed, unsigned long long traj,
-                                                unsigned long long step, double &u1, double &u2)
-{
-    unsigned int c0 = (unsigned int)step, c1 = (unsigned int)(step >> 32);
-    unsigned int c2 = (unsigned int)traj, c3 = (unsigned int)(traj >> 32);
-    unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned int h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const unsigned int h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        const unsigned int n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    const unsigned long long a = ((unsigned long long)(c0 >> 5) << 26) + (c1 >> 6);
-    const unsigned long long b = ((unsigned long long)(c2 >> 5) << 26) + (c3 >> 6);
-    u1 = (double)a * (1.0 / 9007199254740992.0);
-    u2 = (double)(b + 1) * (1.0 / 9007199254740992.0);
-}
-
-constexpr double TIE_TOL = 1e-12;  // >> n_proc*eps: scan-order differences cannot cross it
 
 // A lattice site as the kernel carries it: index + (compact layout) packed cell/basis.
 struct Site {
@@ -1243,9 +1155,68 @@ __global__ void neigh_pack_kernel(const int *neigh, const unsigned *site_pack, l
     if (i < n) out[i] = site_pack[neigh[i]];
 }
 
+// H entries of the cell-0 basis sites: one thread per (b_a, delta, b_y)
+__global__ void stencil_table_kernel(const double *__restrict__ Pu, long long n_sites, int n_basis, int sx, int sy,
+                                     int sz, int ncb, int nn, int nnp, const int *__restrict__ cb_all,
+                                     const int *__restrict__ nb_all, const int *__restrict__ nb_cell,
+                                     double *__restrict__ H)
+{
+    const int wy = 2 * sy - 1, wz = 2 * sz - 1;
+    const long long n_delta = (long long)(2 * sx - 1) * wy * wz;
+    const long long total = (long long)ncb * n_delta * ncb;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int by = (int)(i % ncb);
+    const long long r = i / ncb;
+    const long long dl = r % n_delta;
+    const int ba = (int)(r / n_delta);
+    const int iz = (int)(dl % wz), iy = (int)((dl / wz) % wy), ix = (int)(dl / ((long long)wz * wy));
+    const int cx = (ix + 1) % sx, cy = (iy + 1) % sy, cz = (iz + 1) % sz;   // (d + s) mod s, d = i - (s - 1)
+    const int a_all = cb_all[ba], y_all = cb_all[by];
+    const double pay = Pu[(long long)a_all * n_sites + ((long long)(cx * sy + cy) * sz + cz) * n_basis + y_all];
+    double *out = H + i * nnp;
+    for (int d = 0; d < nnp; ++d) {
+        double v = 0.0;
+        if (d < nn) {
+            const int n_all = nb_all[ba * nn + d];
+            const int *nc = nb_cell + (ba * nn + d) * 3;
+            const int rx = (cx - nc[0] + sx) % sx, ry = (cy - nc[1] + sy) % sy, rz = (cz - nc[2] + sz) % sz;
+            const double pny = Pu[(long long)n_all * n_sites + ((long long)(rx * sy + ry) * sz + rz) * n_basis + y_all];
+            v = __dsub_rn(pny, pay);
+        }
+        out[d] = v;
+    }
+}
+
+// per-(basis, direction) constants: everything of a process except the carrier sum
+__global__ void stencil_const_kernel(const double *__restrict__ Pu, long long n_sites, int n_basis, int sy, int sz,
+                                     int ncb, int nn, const int *__restrict__ cb_all, const int *__restrict__ nb_all,
+                                     const int *__restrict__ nb_cell, const double *__restrict__ v_lat,
+                                     const double *__restrict__ e_rel, const int *__restrict__ site_class,
+                                     const double *__restrict__ lam, const double *__restrict__ vab,
+                                     const double *__restrict__ i4l, double qc, double *__restrict__ cst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncb * nn) return;
+    const int b = i / nn, d = i - b * nn;
+    const int a_all = cb_all[b], n_all = nb_all[i];
+    const int *nc = nb_cell + i * 3;
+    const long long n_site = ((long long)(nc[0] * sy + nc[1]) * sz + nc[2]) * n_basis + n_all;
+    const double paa = Pu[(long long)a_all * n_sites + a_all];
+    const double pab = Pu[(long long)a_all * n_sites + n_site];
+    const int cls = site_class[a_all];
+    double *o = cst + (long long)b * ST_ROWS * nn + d;
+    o[ST_T02 * nn] = __dmul_rn(qc, __dsub_rn(paa, pab));                 // core.py:2010-2014
+    o[ST_SHIFT * nn] = __dsub_rn(e_rel[n_site], e_rel[a_all]);           // core.py:2023-2025
+    o[ST_LAM * nn] = lam[cls * nn + d];
+    o[ST_VAB * nn] = vab[cls * nn + d];
+    o[ST_I4L * nn] = i4l[cls * nn + d];
+    o[ST_VL * nn] = __dsub_rn(v_lat[n_all], v_lat[a_all]);
+}
+
 }  // namespace pycd
 
-#include "kmc_stencil.cuh"
+#include "kmc_stencil_launch.h"
 
 using namespace pycd;
 
@@ -1261,6 +1232,7 @@ struct pycd_kmc_system {
     DevBuf<unsigned> site_pack, neigh_pack, neigh2_pack;
     DevBuf<int> neigh2;
     bool compact = false;
+    std::vector<int> site_centre_h;   // host copy: validates every occupancy array that reaches the device
     // lattice-stencil tables (kmc_stencil.cuh); stencil_why says why they are absent
     StencilDev st{};
     bool stencil_ok = false;
@@ -1268,7 +1240,7 @@ struct pycd_kmc_system {
     size_t st_smem = 0;
     DevBuf<double> st_H, st_cst;
     DevBuf<int> st_ctr_key, st_ctr_site, st_nbr_key, st_nbr_ctr, st_cb_all, st_nb_all, st_nb_cell;
-    DevBuf<unsigned> st_perm;
+    DevBuf<unsigned long long> st_perm;
 };
 
 struct pycd_kmc_ensemble {
@@ -1281,7 +1253,29 @@ struct pycd_kmc_ensemble {
     DevBuf<long long> start_idx, n_steps, near_tie, clamped;
     std::string last_kernel;
     long long n_active = -1;   // unfinished trajectories after the last advance (-1: all)
+    // pipelined read-back (pycd_kmc_read_begin / _end): the grid being copied out while the next batch
+    // fills the other one, and snapshots of the small per-trajectory state
+    DevBuf<double> unwrapped_alt, snap_t, snap_drift;
+    DevBuf<long long> snap_n_steps, snap_near_tie, snap_clamped;
+    DevBuf<int> snap_occ;
+    cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    bool read_in_flight = false;
+    bool needs_reset = false;   // the displacement grid was handed to a pipelined read: re-arm before advancing
+    ~pycd_kmc_ensemble() {
+        if (ev_snap) cudaEventDestroy(ev_snap);
+        if (ev_copied) cudaEventDestroy(ev_copied);
+    }
 };
+
+// occupancy arrays index device tables: every entry must be a site of the carrier's element
+static void validate_occupancy(const pycd_kmc_system *sys, const int32_t *occ, size_t count, std::vector<int> &host) {
+    host.resize(count);
+    PYCD_CUDA(cudaMemcpy(host.data(), occ, sizeof(int) * count,
+                         is_device_pointer(occ) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+    const long long n = sys->dev.n_sites;
+    for (int v : host)
+        PYCD_REQUIRE(v >= 0 && v < n && sys->site_centre_h[v] >= 0, "occupancy entry is not a carrier site");
+}
 
 // energy outputs at t = 0: energy_array[0] = initial energy, everything else 0 (core.py:2715-2718, 2782-2783)
 static void arm_energy(pycd_kmc_ensemble *ens, cudaStream_t s);
@@ -1299,7 +1293,7 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
     const int sx = d->size[0], sy = d->size[1], sz = d->size[2];
     const long long cells = (long long)sx * sy * sz;
     auto need = [](bool ok, const char *why) { if (!ok) throw Error(why); };
-    need(nn <= 8, "more than 8 neighbour slots");
+    need(nn == 4 || nn == 8 || nn == 12, "stencil kernels are instantiated for 4, 8 and 12 neighbour slots");
     need(nc < (1 << 24) && nc % cells == 0, "centre count is not a multiple of the cell count");
     const int ncb = (int)(nc / cells);
     need(ncb >= 1 && ncb <= 127, "more than 127 carrier sites per unit cell");
@@ -1362,7 +1356,7 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
             cell_xyz(ns / nb, &nb_cell[(size_t)(b * nn + k) * 3]);
         }
     std::vector<int> ctr_key((size_t)nc), nbr_key((size_t)nc * nn), nbr_ctr((size_t)nc * nn);
-    std::vector<unsigned> perm((size_t)nc);
+    std::vector<unsigned long long> perm((size_t)nc);
     const int size[3] = {sx, sy, sz};
     for (long long e = 0; e < nc; ++e) {
         const int b = (int)(e % ncb);
@@ -1371,7 +1365,8 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
         ctr_key[e] = key_of(e);
         const int cls = site_class[ctr_site[e]];
         need(cls >= 0 && cls < d->n_class, "bad site class");
-        unsigned used = 0, pm = 0;
+        unsigned used = 0;
+        unsigned long long pm = 0;
         for (int k = 0; k < nn; ++k) {
             const int ns = neigh[(size_t)e * nn + k];
             need(ns >= 0 && ns < n && site_centre[ns] >= 0, "neighbour is not a carrier site");
@@ -1392,7 +1387,7 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
             }
             need(found >= 0, "neighbour lists are not translations of those of unit cell 0");
             used |= 1u << found;
-            pm |= (unsigned)k << (4 * found);
+            pm |= (unsigned long long)k << (4 * found);
             const int e2 = site_centre[ns];
             nbr_key[(size_t)e * nn + k] = key_of(e2);
             nbr_ctr[(size_t)e * nn + k] = e2 | ((e2 % ncb) << 24);
@@ -1408,7 +1403,7 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
     up_i(sys->st_nbr_ctr, nbr_ctr); up_i(sys->st_cb_all, cb_all); up_i(sys->st_nb_all, nb_all);
     up_i(sys->st_nb_cell, nb_cell);
     sys->st_perm.alloc(perm.size());
-    PYCD_CUDA(cudaMemcpyAsync(sys->st_perm.p, perm.data(), sizeof(unsigned) * perm.size(), cudaMemcpyHostToDevice, s));
+    PYCD_CUDA(cudaMemcpyAsync(sys->st_perm.p, perm.data(), sizeof(unsigned long long) * perm.size(), cudaMemcpyHostToDevice, s));
     sys->st_H.alloc((size_t)entries * nnp);
     sys->st_cst.alloc((size_t)ncb * ST_ROWS * nn);
     stencil_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(
@@ -1441,6 +1436,7 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
         PYCD_REQUIRE(d->P && d->site_centre && d->site_class && d->neigh && d->hopvec && d->lam &&
                          d->vab && d->e_rel && d->q_lat, "NULL table");
         PYCD_REQUIRE(d->kT > 0 && d->vn > 0, "bad kT / vn");
+        NvtxRange nvtx("pycd.kmc_system_create");
         DeviceGuard g(ctx);
         auto sys = new pycd_kmc_system();
         try {
@@ -1471,6 +1467,18 @@ extern "C" int pycd_kmc_system_create(pycd_ctx *ctx, const pycd_kmc_system_desc 
             sys->lam.bind(d->lam, (size_t)d->n_class * d->nn, s);
             sys->vab.bind(d->vab, (size_t)d->n_class * d->nn, s);
             sys->e_rel.bind(d->e_rel, n, s);
+            {   // the neighbour table is dereferenced by setup kernels and step kernels: range-check it
+                const size_t nn_tot = (size_t)d->n_centres * d->nn;
+                std::vector<int> neigh_h(nn_tot);
+                sys->site_centre_h.resize(n);
+                PYCD_CUDA(cudaStreamSynchronize(s));
+                PYCD_CUDA(cudaMemcpy(neigh_h.data(), sys->neigh.p, sizeof(int) * nn_tot, cudaMemcpyDeviceToHost));
+                PYCD_CUDA(cudaMemcpy(sys->site_centre_h.data(), sys->site_centre.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+                for (int v : sys->site_centre_h) PYCD_REQUIRE(v >= -1 && v < d->n_centres, "site_centre entry out of range");
+                for (int v : neigh_h)
+                    PYCD_REQUIRE(v >= 0 && (size_t)v < n && sys->site_centre_h[v] >= 0,
+                                 "neigh entry is not a site of the carrier's element");
+            }
             if (sys->compact) {
                 const long long nn_tot = (long long)d->n_centres * d->nn;
                 sys->neigh_pack.alloc((size_t)nn_tot);
@@ -1580,13 +1588,8 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
         const long long n_proc_ll = (long long)C * sys->dev.nn;
         PYCD_REQUIRE(n_proc_ll <= 2560, "more than 2560 processes per trajectory is not supported");
         // validate initial sites on the host copy (they index device tables)
-        std::vector<int> occ_h((size_t)nt * C);
-        PYCD_CUDA(cudaMemcpy(occ_h.data(), d->occupancy0, sizeof(int) * nt * C,
-                             is_device_pointer(d->occupancy0) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
-        std::vector<int> sc((size_t)sys->dev.n_sites);
-        PYCD_CUDA(cudaMemcpy(sc.data(), sys->dev.site_centre, sizeof(int) * sys->dev.n_sites, cudaMemcpyDeviceToHost));
-        for (int v : occ_h)
-            PYCD_REQUIRE(v >= 0 && v < sys->dev.n_sites && sc[v] >= 0, "initial occupancy is not a carrier site");
+        std::vector<int> occ_h;
+        validate_occupancy(sys, d->occupancy0, (size_t)nt * C, occ_h);
         auto ens = new pycd_kmc_ensemble();
         try {
             ens->sys = sys;
@@ -1706,6 +1709,8 @@ extern "C" int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *oc
         EnsDev &E = ens->dev;
         const size_t nt = (size_t)E.n_traj;
         cudaStream_t s = ctx->stream;
+        std::vector<int> occ_h;
+        validate_occupancy(ens->sys, occupancy0, nt * E.C, occ_h);
         PYCD_CUDA(cudaMemcpyAsync(ens->occ.p, occupancy0, sizeof(int) * nt * E.C, cudaMemcpyDefault, s));
         ens->done.zero(s); ens->t.zero(s); ens->disp.zero(s); ens->row.zero(s); ens->drift.zero(s);
         ens->rates.zero(s); ens->n_steps.zero(s); ens->near_tie.zero(s); ens->clamped.zero(s);
@@ -1714,6 +1719,7 @@ extern "C" int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *oc
         PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
         E.traj_id0 = traj_id0;
         ens->n_active = -1;
+        ens->needs_reset = false;
         arm_energy(ens, s);
         PYCD_CUDA(cudaStreamSynchronize(s));
     });
@@ -1723,6 +1729,7 @@ extern "C" int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens) {
     return guarded([&] {
         if (!ens) return;
         DeviceGuard g(ens->sys->ctx);
+        if (ens->read_in_flight) cudaEventSynchronize(ens->ev_copied);
         delete ens;
     });
 }
@@ -1743,26 +1750,15 @@ static void launch_step(pycd_ctx *ctx, bool compact, const SysDev &S, const EnsD
     else launch_step_impl<BS, false, 0, 0>(ctx, S, E, A, smem);
 }
 
-// kmc_step_warp_kernel is compiled per mode: INCR (refresh_interval > 1) and PLAIN (no field, no energy
-// outputs, no per-step event / time outputs), so that the production shape carries none of those tests
-template <int NWC, int CPL, int NN>
-static void launch_warp_step(pycd_ctx *ctx, unsigned grid, size_t smem, const SysDev &S, const StencilDev &T,
-                             const EnsDev &E, const AdvanceArgs &A) {
-    const bool incr = E.refresh_interval > 1;
-    const bool plain = !E.energy && !S.field_active && !E.field_traj && !A.events_out && !A.times_out;
-    const unsigned bs = 32 * NWC;
-    if (incr && plain) kmc_step_warp_kernel<NWC, CPL, NN, true, true><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
-    else if (incr) kmc_step_warp_kernel<NWC, CPL, NN, true, false><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
-    else if (plain) kmc_step_warp_kernel<NWC, CPL, NN, false, true><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
-    else kmc_step_warp_kernel<NWC, CPL, NN, false, false><<<grid, bs, smem, ctx->stream>>>(S, T, E, A);
-}
-
 extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
                                 int32_t *events_out, double *times_out, int64_t *steps_done,
                                 int64_t *n_active) {
     return guarded([&] {
         PYCD_REQUIRE(ens, "NULL ensemble");
         PYCD_REQUIRE(max_steps > 0, "max_steps must be positive");
+        PYCD_REQUIRE(!ens->needs_reset, "the ensemble's grid was handed to pycd_kmc_read_begin: call "
+                                        "pycd_kmc_ensemble_reset before advancing again");
+        NvtxRange nvtx("pycd.kmc_advance");
         pycd_ctx *ctx = ens->sys->ctx;
         DeviceGuard g(ctx);
         EnsDev &E = ens->dev;
@@ -1795,10 +1791,12 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         const char *kv = getenv("PYCD_KMC_VARIANT");
         const bool per_process = kv && std::string(kv) == "process";
         const std::string variant = kv ? kv : "";
-        // doped ensembles carry per-trajectory site tables: the lattice-stencil constants and the carrier
-        // kernel's lookups are per system, so they run on the generic gather kernel
+        // the lattice-stencil kernels cover full-PBC systems with 4 / 8 / 12 neighbour slots; doped
+        // ensembles (per-trajectory site energies / lattice potential) run on their featured variant
         const bool doped = E.v_lat_traj != nullptr;
-        const bool use_stencil = !doped && cp && ens->sys->stencil_ok && ens->sys->dev.nn == 4 && E.C <= 64 &&
+        const int nn_sys = ens->sys->dev.nn;
+        const int c_max = (nn_sys == 4) ? 128 : 64;
+        const bool use_stencil = cp && ens->sys->stencil_ok && E.C <= c_max &&
                                  (variant.empty() || variant == "stencil" || variant == "stencil_1warp");
         if (variant == "stencil" && !use_stencil)
             throw Error("PYCD_KMC_VARIANT=stencil: stencil kernel unavailable (" +
@@ -1807,20 +1805,28 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         int bs_force = 0;   // diagnostic: PYCD_KMC_BS forces the block size of the generic kernel
         if (const char *e = getenv("PYCD_KMC_BS")) bs_force = atoi(e);
         if (use_stencil && bs_force == 0) {
-            // one warp per trajectory over the lattice-stencil table (kmc_stencil.cuh)
+            // one CTA of one or two warps per trajectory over the lattice-stencil table (kmc_stencil.cuh)
             const unsigned g = (unsigned)E.n_traj;
             const size_t sm = ens->sys->st_smem;
             // small ensembles (a few trajectories per SM) are bound by the latency of a step: two warps
             // per trajectory; large ones by instructions per step: one warp, two carriers per lane
             // (finished trajectories leave their CTA at once, so the ACTIVE count decides)
             const long long live = ens->n_active >= 0 ? ens->n_active : (long long)E.n_traj;
-            const bool wide = E.C > 32 && live <= 4ll * ctx->n_sm && variant != "stencil_1warp";
-            if (E.C <= 32) launch_warp_step<1, 1, 4>(ctx, g, sm, ens->sys->dev, ens->sys->st, E, A);
-            else if (wide) launch_warp_step<2, 1, 4>(ctx, g, sm, ens->sys->dev, ens->sys->st, E, A);
-            else launch_warp_step<1, 2, 4>(ctx, g, sm, ens->sys->dev, ens->sys->st, E, A);
-            const int nwc = wide ? 2 : 1, cpl = (E.C <= 32 || wide) ? 1 : 2;
+            int nwc, cpl;
+            if (E.C <= 32) { nwc = 1; cpl = 1; }
+            else if (E.C <= 64) {
+                const bool wide = nn_sys != 4 || (live <= 4ll * ctx->n_sm && variant != "stencil_1warp");
+                nwc = wide ? 2 : 1;
+                cpl = wide ? 1 : 2;
+            } else { nwc = 2; cpl = 2; }
+            bool ok = false;
+            if (nn_sys == 4) ok = stencil_launch_nn4(ctx, nwc, cpl, g, sm, ens->sys->dev, ens->sys->st, E, A);
+            else if (nn_sys == 8) ok = stencil_launch_nn8(ctx, nwc, cpl, g, sm, ens->sys->dev, ens->sys->st, E, A);
+            else if (nn_sys == 12) ok = stencil_launch_nn12(ctx, nwc, cpl, g, sm, ens->sys->dev, ens->sys->st, E, A);
+            if (!ok) throw Error("stencil kernel shape not instantiated");
             check_launch(ctx, "kmc_step_warp_kernel");
-            ens->last_kernel = "kmc_step_warp_kernel<" + std::to_string(nwc) + "," + std::to_string(cpl) + ",4>";
+            ens->last_kernel = "kmc_step_warp_kernel<" + std::to_string(nwc) + "," + std::to_string(cpl) + "," +
+                               std::to_string(nn_sys) + ">";
         }
         else if (bs_force == 32) launch_step<32>(ctx, cp, ens->sys->dev, E, A, smem);
         else if (bs_force == 64) launch_step<64>(ctx, cp, ens->sys->dev, E, A, smem);
@@ -1889,13 +1895,74 @@ extern "C" int pycd_kmc_read(pycd_kmc_ensemble *ens, double *unwrapped, int64_t 
     });
 }
 
-#ifdef PYCD_TRACE
-extern "C" int pycd_debug_trace(long long *out) {
+
+// Pipelined read-back.  The state after the launches issued so far is snapshotted on the compute stream;
+// the ensemble switches to its second displacement grid, and the copy stream moves the snapshot to the
+// HOST buffers while the caller re-arms the ensemble and runs the next batch.
+extern "C" int pycd_kmc_read_begin(pycd_kmc_ensemble *ens, double *unwrapped, int64_t *n_steps, double *sim_time,
+                                   int32_t *occupancy, double *drift, int64_t *near_tie, int64_t *clamped) {
     return guarded([&] {
-        PYCD_CUDA(cudaMemcpyFromSymbol(out, g_st_trace, sizeof(long long) * 256 * 16 * 16));
+        PYCD_REQUIRE(ens, "NULL ensemble");
+        PYCD_REQUIRE(!ens->read_in_flight, "a pipelined read is in flight: call pycd_kmc_read_end first");
+        PYCD_REQUIRE(!ens->energy.p, "pipelined read-back is not available with energy outputs");
+        pycd_ctx *ctx = ens->sys->ctx;
+        DeviceGuard g(ctx);
+        EnsDev &E = ens->dev;
+        const size_t nt = (size_t)E.n_traj, C = (size_t)E.C;
+        cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+        if (!ens->ev_snap) {
+            PYCD_CUDA(cudaEventCreateWithFlags(&ens->ev_snap, cudaEventDisableTiming));
+            PYCD_CUDA(cudaEventCreateWithFlags(&ens->ev_copied, cudaEventDisableTiming));
+            ens->snap_t.alloc(nt); ens->snap_drift.alloc(nt * 3 * C); ens->snap_n_steps.alloc(nt);
+            ens->snap_near_tie.alloc(nt); ens->snap_clamped.alloc(nt); ens->snap_occ.alloc(nt * C);
+        }
+        const double *grid = nullptr;
+        if (unwrapped) {
+            PYCD_REQUIRE(ens->unwrapped.p, "ensemble was created without record_unwrapped");
+            if (!ens->unwrapped_alt.p) {
+                ens->unwrapped_alt.alloc(ens->unwrapped.n);
+                ens->unwrapped_alt.zero(s);
+            }
+            grid = ens->unwrapped.p;
+            std::swap(ens->unwrapped.p, ens->unwrapped_alt.p);   // the next batch fills the other grid
+            E.unwrapped = ens->unwrapped.p;
+            ens->needs_reset = true;
+        }
+        auto snap = [&](void *dst, const void *src, size_t bytes) {
+            PYCD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+        };
+        snap(ens->snap_t.p, ens->t.p, sizeof(double) * nt);
+        snap(ens->snap_drift.p, ens->drift.p, sizeof(double) * nt * 3 * C);
+        snap(ens->snap_n_steps.p, ens->n_steps.p, sizeof(long long) * nt);
+        snap(ens->snap_near_tie.p, ens->near_tie.p, sizeof(long long) * nt);
+        snap(ens->snap_clamped.p, ens->clamped.p, sizeof(long long) * nt);
+        snap(ens->snap_occ.p, ens->occ.p, sizeof(int) * nt * C);
+        PYCD_CUDA(cudaEventRecord(ens->ev_snap, s));
+        PYCD_CUDA(cudaStreamWaitEvent(cs, ens->ev_snap, 0));
+        auto pull = [&](void *dst, const void *src, size_t bytes) {
+            if (dst) PYCD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cs));
+        };
+        pull(unwrapped, grid, sizeof(double) * nt * E.n_path * 3 * C);
+        pull(n_steps, ens->snap_n_steps.p, sizeof(long long) * nt);
+        pull(sim_time, ens->snap_t.p, sizeof(double) * nt);
+        pull(occupancy, ens->snap_occ.p, sizeof(int) * nt * C);
+        pull(drift, ens->snap_drift.p, sizeof(double) * nt * 3 * C);
+        pull(near_tie, ens->snap_near_tie.p, sizeof(long long) * nt);
+        pull(clamped, ens->snap_clamped.p, sizeof(long long) * nt);
+        PYCD_CUDA(cudaEventRecord(ens->ev_copied, cs));
+        ens->read_in_flight = true;
     });
 }
-#endif
+
+extern "C" int pycd_kmc_read_end(pycd_kmc_ensemble *ens) {
+    return guarded([&] {
+        PYCD_REQUIRE(ens, "NULL ensemble");
+        if (!ens->read_in_flight) return;
+        DeviceGuard g(ens->sys->ctx);
+        PYCD_CUDA(cudaEventSynchronize(ens->ev_copied));
+        ens->read_in_flight = false;
+    });
+}
 
 extern "C" int pycd_kmc_last_kernel(pycd_kmc_ensemble *ens, char *buf, int32_t n) {
     return guarded([&] {

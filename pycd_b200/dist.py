@@ -48,17 +48,62 @@ def allgather_rows(full, group=None):
     return full
 
 
+def ensure_process_group(local_rank=0):
+    """Initialises torch.distributed from the torchrun environment when WORLD_SIZE > 1 and nobody did
+    yet: NCCL on the GPU box (one process per GPU), gloo in CPU tests (PYCD_DIST_BACKEND overrides)."""
+    import os
+    if int(os.environ.get('WORLD_SIZE', '1')) <= 1 or is_initialized():
+        return
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    backend = os.environ.get('PYCD_DIST_BACKEND') or ('nccl' if torch.cuda.is_available() else 'gloo')
+    if backend == 'nccl':
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    else:
+        dist.init_process_group(backend)
+
+
+def barrier():
+    if is_initialized():
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def _comm_device(device=None):
+    import torch
+    import torch.distributed as dist
+    if device is not None:
+        return device
+    if dist.get_backend() == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
 def gather_trajectory_arrays(local, n_total, device=None, group=None):
     """Concatenates per-rank (n_local, ...) numpy arrays in rank order -> (n_total, ...) on
-    every rank (trajectory blocks from `block`)."""
+    every rank (trajectory blocks from `block`): one all_gather of blocks padded to the largest."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = np.ascontiguousarray(local)
     tail = local.shape[1:]
-    out = torch.zeros((n_total,) + tail, dtype=torch.from_numpy(local).dtype, device=device)
     lo, hi = block(rank, world, n_total)
     assert hi - lo == local.shape[0], 'local block does not match the trajectory partition'
-    out[lo:hi] = torch.from_numpy(local).to(out.device)
-    dist.all_reduce(out, group=group)  # disjoint blocks: the sum is the concatenation
-    return out.cpu().numpy()
+    width = max(block(g, world, n_total)[1] - block(g, world, n_total)[0] for g in range(world))
+    dev = _comm_device(device)
+    mine = torch.zeros((width,) + tail, dtype=torch.from_numpy(local).dtype, device=dev)
+    mine[:hi - lo] = torch.from_numpy(local).to(dev)
+    out = torch.empty((world * width,) + tail, dtype=mine.dtype, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=group)
+    out = out.view((world, width) + tail).cpu().numpy()
+    return np.concatenate([out[g, :block(g, world, n_total)[1] - block(g, world, n_total)[0]]
+                           for g in range(world)], axis=0)
+
+
+def gather_blocks(local, n_total, local_rank=0):
+    """gather_trajectory_arrays for drivers launched under torchrun (creates the process group on
+    first use)."""
+    ensure_process_group(local_rank)
+    return gather_trajectory_arrays(local, n_total)

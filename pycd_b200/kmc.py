@@ -112,12 +112,13 @@ class RunParameters:
         return occ
 
 
-def write_initial_rnd_states(dst_path, n_traj, random_seed):
-    """Run.preproduction, core.py:2573-2580: per-trajectory MT19937 states."""
+def write_initial_rnd_states(dst_path, n_traj, random_seed, only=None):
+    """Run.preproduction, core.py:2573-2580: per-trajectory MT19937 states.  `only`: the trajectory
+    indices this process writes (a rank's block under torchrun); the seeds are those of the full run."""
     rng = _random.Random()
     rng.seed(random_seed)
     seeds = [rng.random() for _ in range(n_traj)]
-    for i in range(n_traj):
+    for i in (range(n_traj) if only is None else only):
         d = dst_path / f'traj{i + 1}'
         d.mkdir(parents=True, exist_ok=True)
         rng.seed(seeds[i])
@@ -359,6 +360,19 @@ class KmcEnsemble:
         out['unwrapped'] = uw
         out['rates'] = rt
         return out
+
+    def read_begin(self, out):
+        """Pipelined read-back into the (pinned) buffers of `out` (pinned_buffers()): returns at once;
+        reset() + advance of the next batch overlap the copy; read_end() completes it."""
+        uw = out.get('unwrapped') if self.record_unwrapped else None
+        nat.check(nat.lib().pycd_kmc_read_begin(self.handle, nat.ptr(uw), nat.ptr(out['n_steps']),
+                                                nat.ptr(out['time']), nat.ptr(out['occupancy']),
+                                                nat.ptr(out['drift']), nat.ptr(out['near_tie']),
+                                                nat.ptr(out['clamped'])))
+        return out
+
+    def read_end(self):
+        nat.check(nat.lib().pycd_kmc_read_end(self.handle))
 
     def pinned_buffers(self):
         """Result buffers in page-locked host memory, to be passed as read(out=...)."""

@@ -1,5 +1,6 @@
 """Drop-in for PyCD/material_setup.py:13-85: neighbour list, pair vectors and the Ewald
 precomputed array, with the N^2*K arithmetic on the GPU."""
+import os
 from datetime import datetime
 
 import numpy as np
@@ -10,6 +11,9 @@ from .config import load_material_parameters
 from .fileio import generate_report
 from .lattice import Lattice, Supercell
 from .tables import save_hop_neighbor_list
+
+# rows of unit cell 0, (n_per_cell, N) f64: written for pbc = [1, 1, 1], read by material_run
+UNIT_ROWS_FILE = 'precomputed_array_unit_rows.npy'
 
 
 def material_setup(input_directory_path, system_size, pbc, generate_hop_neighbor_list,
@@ -38,14 +42,35 @@ def material_setup(input_directory_path, system_size, pbc, generate_hop_neighbor
                                       'of the accelerated path')
         start = datetime.now()
         ep = ew.EwaldParameters(supercell, params.alpha, params.r_cut, params.k_cut)
-        ctx = nat.default_context()
-        P, _ = ew.precomputed_array(ctx, ep)
+        ctx = nat.default_context(int(os.environ.get('LOCAL_RANK', '0')))
+        opts = getattr(params, 'b200', None) or {}
+        n = supercell.num_system_elements
+        symmetric = ew.can_use_translation_symmetry(supercell)
+        # Full PBC: the rows of unit cell 0 determine the whole array.  They are written
+        # next to the reference's file; material_run prefers them (L2-resident table, stencil kernel).
+        # The dense N x N file stays the exchange format with the reference and is written unless it would
+        # exceed b200.dense_limit_gb (default 4; 7.2 GB at Hematite 10x10x10).
+        limit = float(opts.get('dense_limit_gb', 4.0)) * 1e9
+        want_dense = (not symmetric) or n * n * 8 <= limit
+        P = None
+        if symmetric:
+            p_unit, _ = ew.ewald_rows(ctx, ep, np.ascontiguousarray(supercell.coordinates), 0,
+                                      supercell.n_per_cell)
+            np.save(input_directory_path / UNIT_ROWS_FILE, p_unit)
+            if want_dense:
+                P = ew.ewald_expand(ctx, supercell, p_unit, 0, n)
+        else:
+            P, _ = ew.precomputed_array(ctx, ep, symmetric=False)
         energies = None
         if compute_energy_contributions:
+            if P is None:
+                raise NotImplementedError('compute_energy_contributions needs the dense array; raise '
+                                          'b200.dense_limit_gb in sys_config.yml or pass 0')
             energies = energy_contributions(ctx, ep, P)
         generate_report(start, input_directory_path, 'precomputed_array', 1,
                         ''.join(ew.log_prefix(ep, energies)))
-        np.save(input_directory_path / 'precomputed_array.npy', P)
+        if P is not None:
+            np.save(input_directory_path / 'precomputed_array.npy', P)
     return None
 
 

@@ -191,7 +191,9 @@ def test_doped_ensemble_matches_oracle_fresh_geometry(ctx, layout, refresh):
     while ens.advance_resident(496) > 0:
         pass
     got = ens.read()
-    assert ens.last_kernel() == 'kmc_step_kernel'
+    # BVO electrons in a 3x3x2 cell: 8 neighbour slots; the unit-rows layout runs the lattice-stencil kernel
+    # (doped trajectories read their site energies / lattice potential per site), the dense layout the gathers
+    assert ens.last_kernel() == ('kmc_step_warp_kernel<1,1,8>' if layout == 'unit_rows' else 'kmc_step_kernel')
     ens.close()
     system.close()
     for i in range(n_traj):
@@ -269,6 +271,10 @@ def test_unit_rows_layout_matches_oracle_on_expanded_array(ctx, case, refresh):
     while ens.advance_resident(400) > 0:
         pass
     got = ens.read()
+    # Hematite electrons: 4 slots; BVO holes: 12 slots, two site classes -- both on the lattice-stencil kernel
+    assert system.stencil_info()[0], system.stencil_info()
+    assert ens.last_kernel() == {'hematite_3x3x2_12e': 'kmc_step_warp_kernel<1,1,4>',
+                                 'bvo_3x3x1_6h': 'kmc_step_warp_kernel<1,1,12>'}[case]
     # re-armed ensemble reproduces itself
     ens.reset(occ)
     while ens.advance_resident(2000) > 0:
@@ -383,7 +389,7 @@ def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
     assert np.allclose(gg[3], one['dg0_grid'], rtol=1e-9, atol=1e-15)
 
 
-@pytest.mark.parametrize('carriers', [5, 33, 64])
+@pytest.mark.parametrize('carriers', [5, 33, 64, 100])
 def test_stencil_kernel_equals_gather_kernels(ctx, hematite_64e, carriers, monkeypatch):
     """The lattice-stencil kernel (one H[b_a][delta][b_y][slot] entry per carrier pair) against the
     element-gather kernels on the same unit-row table: stateless mode bit-identical (rates, times,
@@ -484,6 +490,83 @@ def test_64_carriers_replay_and_first_step_rates(ctx, hematite_64e):
         assert np.array_equal(res['events'][i, :n], ref['events'])
         assert np.allclose(res['times'][i, :n], ref['times'][1:], rtol=1e-12, atol=0)
         assert np.array_equal(got['unwrapped'][i], ref['unwrapped'])
+
+
+def _bvo_fresh(ctx, size, species):
+    """BVO supercell with fresh geometry: run parameters, unit-cell rows and the expanded dense array."""
+    from pycd_b200.kmc import RunParameters
+    from pycd_b200.lattice import Supercell
+    ex = H.load_example('bvo')
+    sim = ex.sim
+    sc = Supercell(ex.lattice, size, [1, 1, 1])
+    run = RunParameters(ex.lattice, sc, sc.hop_neighbor_tables(), sim['temp'], 'full', 'full',
+                        sim['t_final'], sim['time_interval'], species, {}, sim['relative_energies'],
+                        sim['external_field'])
+    ep = EW.EwaldParameters(sc, ex.cfg['alpha'], ex.cfg['r_cut'], ex.cfg['k_cut'])
+    p_unit, _ = EW.ewald_rows(ctx, ep, np.ascontiguousarray(sc.coordinates), 0, sc.n_per_cell)
+    dense = EW.ewald_expand(ctx, sc, p_unit, 0, sc.num_system_elements)
+    return run, p_unit, dense
+
+
+@pytest.mark.parametrize('refresh', [1, 16])
+@pytest.mark.parametrize('case', ['cfg2_perf_4x4x2_16e', 'bvo_3x3x2_40e', 'bvo_3x3x2_40h'])
+def test_stencil_kernel_bvo_shapes_match_oracle(ctx, case, refresh):
+    """BASELINE config 2, performance variant (BVO 4x4x2, N = 768, 8 neighbours per V, 16
+    electrons, fresh geometry) and the two-warp shapes of the 8-slot (V:V electrons) and 12-slot (O:O holes,
+    two site classes, core.py:1961-1970) stencil kernels against the oracle on the expanded dense array."""
+    size, species, kernel = {'cfg2_perf_4x4x2_16e': ([4, 4, 2], [16, 0], 'kmc_step_warp_kernel<1,1,8>'),
+                             'bvo_3x3x2_40e': ([3, 3, 2], [40, 0], 'kmc_step_warp_kernel<2,1,8>'),
+                             'bvo_3x3x2_40h': ([3, 3, 2], [0, 40], 'kmc_step_warp_kernel<2,1,12>')}[case]
+    run, p_unit, dense = _bvo_fresh(ctx, size, species)
+    assert run.tables.nn == (8 if species[0] else 12)
+    n_traj, steps = 12, 1600
+    occ = K.philox_initial_occupancy(run.tables, n_traj, run.n_carriers, seed=31)
+    kw = dict(dt_grid=run.time_interval / 2000, n_path=96, step_limit=steps, stop_at_grid_end=False)
+    system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+    assert system.stencil_info()[0], system.stencil_info()
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=31, refresh_interval=refresh, **kw)
+    res = ens.advance(steps, want_events=True)
+    got = ens.read()
+    assert ens.last_kernel() == kernel
+    ens.close()
+    system.close()
+    orc = O.KmcOracle(run, dense, rng_mode=1, seed=31, **kw)
+    ref = orc.ensemble(occ)
+    assert np.array_equal(got['n_steps'], ref['n_steps'])
+    assert np.array_equal(got['occupancy'], ref['occupancy'])
+    assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+    one = orc.trajectory(occ[5], traj_id=5, want_events=True)
+    assert np.array_equal(res['events'][5, :steps], one['events'][:steps])
+
+
+@pytest.mark.parametrize('refresh', [1, 32])
+def test_stencil_kernel_100_carriers_matches_oracle(ctx, hematite_64e, refresh):
+    """More than 64 carriers: two warps, two carriers per lane (kmc_step_warp_kernel<2,2,4>), field on."""
+    run64, p_unit, dense = hematite_64e
+    from pycd_b200.kmc import RunParameters
+    ex = H.load_example('hematite')
+    field = {'electric': {'active': 1, 'dir': [1, 0, 0], 'ld': 0, 'mag': 1e-3}}
+    run = RunParameters(run64.lattice, run64.supercell, run64.supercell.hop_neighbor_tables(), ex.sim['temp'],
+                        'full', 'full', ex.sim['t_final'], ex.sim['time_interval'], [100, 0], {},
+                        ex.sim['relative_energies'], field)
+    n_traj, steps = 6, 1280
+    occ = K.philox_initial_occupancy(run.tables, n_traj, 100, seed=13)
+    kw = dict(dt_grid=run.time_interval / 8000, n_path=64, step_limit=steps, stop_at_grid_end=False)
+    for with_field in (True, False):   # featured and plain variants
+        system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows', field=None if with_field else np.zeros(3))
+        ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=13, refresh_interval=refresh, **kw)
+        while ens.advance_resident(640) > 0:
+            pass
+        got = ens.read()
+        assert ens.last_kernel() == 'kmc_step_warp_kernel<2,2,4>'
+        ens.close()
+        system.close()
+        ref = O.KmcOracle(run, dense, field=None if with_field else np.zeros(3), rng_mode=1, seed=13, **kw).ensemble(occ)
+        assert np.array_equal(got['n_steps'], ref['n_steps'])
+        assert np.array_equal(got['occupancy'], ref['occupancy'])
+        assert np.array_equal(got['unwrapped'], ref['unwrapped'])
+        if with_field:
+            assert np.allclose(got['drift'], ref['drift'], rtol=1e-9, atol=1e-300)
 
 
 def test_sharding_is_invisible(ctx):
