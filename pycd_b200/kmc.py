@@ -445,6 +445,7 @@ def run_replay(system, rngs, occupancy0, chunk_steps=32768, want_times=True, wan
         if res['n_active'] == 0 or (max_total_steps and total >= max_total_steps):
             break
     state = ens.read()
+    state['last_kernel'] = ens.last_kernel()
     if energy0 is not None:
         state['energy_grid'], state['dg0_grid'] = ens.read_energy()
     ens.close()

@@ -12,8 +12,8 @@ trajectories of a serial run are split into contiguous blocks, one per rank / GP
 own `traj<i>/`, rank 0 writes `drift_mobility.dat` and `Run.log` after the (kB-sized) gather of the drift
 vectors.  Trajectory i uses the same random stream whatever the GPU count.
 """
+import json
 import os
-import random as _random
 from datetime import datetime
 
 import numpy as np
@@ -166,8 +166,10 @@ def material_run(dst_path):
         return doping[i].dopant_site_indices if doping else None
 
     state, times = None, None
+    info = {'rank': rank, 'world': world, 'trajectories': [lo, hi]}
     if n_local:
-        ctx = nat.default_context(local_rank)
+        # PYCD_B200_DEVICE pins the CUDA ordinal (several ranks sharing one GPU in tests)
+        ctx = nat.default_context(int(os.environ.get('PYCD_B200_DEVICE', local_rank)))
         layout, table = select_table(inp, supercell, opts)
         system = kmc.KmcSystem(ctx, run, table, layout=layout)
         rng_kind = opts.get('rng', 'replay')
@@ -190,6 +192,7 @@ def material_run(dst_path):
             if rng_kind == 'replay':
                 state, times, _ = kmc.run_replay(system, rngs, occ, chunk_steps=chunk, want_times=want_times,
                                                  energy0=energy0, doping=doping)
+                info['step_kernel'] = state['last_kernel']
             else:
                 refresh = int(opts.get('refresh_interval', DEFAULT_PHILOX_REFRESH))
                 chunk = max(refresh, chunk - chunk % refresh)
@@ -197,11 +200,18 @@ def material_run(dst_path):
                                       refresh_interval=refresh, energy0=energy0, doping=doping)
                 times = advance_ensemble(ens, chunk, want_times=want_times)
                 state = ens.read()
-                state['last_kernel'] = ens.last_kernel()
+                info['step_kernel'] = ens.last_kernel()
+                info['refresh_interval'] = refresh
                 if want_energy:
                     state['energy_grid'], state['dg0_grid'] = ens.read_energy()
                 ens.close()
+        info.update(p_layout=layout, rng=rng_kind, kmc_steps=int(np.sum(state['n_steps'])),
+                    near_tie_fallbacks=int(np.sum(state['near_tie'])), stencil=system.stencil_info()[0],
+                    device=ctx.device)
         system.close()
+    # sidecar of this implementation (not a reference file): which table / kernel / GPU served the rank
+    with open(dst_path / (f'Run.b200.rank{rank}.json' if world > 1 else 'Run.b200.json'), 'w') as fh:
+        json.dump(info, fh)
 
     n_path, c3 = run.n_path, 3 * run.n_carriers
     for i, d in enumerate(traj_dirs):

@@ -154,3 +154,148 @@ def test_doped_run_consumes_preprod_site_indices(tmp_path):
     for i in range(2):
         assert np.array_equal(np.load(work / f'traj{i + 1}' / 'unwrapped_traj.npy'), z[f'unwrapped_{i}'])
         assert np.allclose(np.load(work / f'traj{i + 1}' / 'time_data.npy'), z[f'time_{i}'], rtol=1e-12, atol=0)
+
+
+def _fast_path_workdir(tmp_path, n_traj=16, size=(4, 4, 4), carriers=64, extra_b200=None):
+    """A fresh PyCD work directory for the ensemble shape of BASELINE config 3 at reduced size: Hematite
+    4x4x4 (N = 1920), 64 electrons, Philox streams."""
+    work = _stage('hematite', tmp_path, {
+        'system_size': list(size), 'species_count': [carriers, 0], 'n_traj': n_traj, 't_final': 1.0e-7,
+        'time_interval': 1.0e-9, 'msd_t_final': 50, 'trim_length': 5, 'random_seed': 7,
+        'b200': dict({'rng': 'philox', 'chunk_steps': 4096}, **(extra_b200 or {}))})
+    inp = work / 'InputFiles'
+    for f in ('hop_neighbor_list.npy', 'precomputed_array.npy', 'precomputed_array.log'):
+        (inp / f).unlink(missing_ok=True)
+    return work, inp
+
+
+def _oracle_of_workdir(work, inp):
+    """The checker's run of the same work directory: oracle on the dense array material_setup wrote."""
+    import oracle as O
+    from pycd_b200 import kmc as K
+    from pycd_b200.config import load_material_parameters, load_simulation_parameters
+    from pycd_b200.lattice import Lattice, Supercell
+    from pycd_b200.tables import load_hop_neighbor_list
+    sim = load_simulation_parameters(work)
+    lat = Lattice(load_material_parameters(inp))
+    sc = Supercell(lat, sim['system_size'], sim['pbc'])
+    run = K.RunParameters(lat, sc, load_hop_neighbor_list(inp / 'hop_neighbor_list.npy'), sim['temp'],
+                          sim['ion_charge_type'], sim['species_charge_type'], sim['t_final'], sim['time_interval'],
+                          sim['species_count'], sim['initial_occupancy'], sim['relative_energies'],
+                          sim['external_field'], sim.get('doping'))
+    occ = K.philox_initial_occupancy(run.tables, int(sim['n_traj']), run.n_carriers, int(sim['random_seed']))
+    dense = np.load(inp / 'precomputed_array.npy')
+    ref = O.KmcOracle(run, dense, rng_mode=1, seed=int(sim['random_seed']), stop_at_grid_end=True).ensemble(occ)
+    return run, ref
+
+
+def test_drivers_reach_the_stencil_kernel_and_match_the_oracle(tmp_path):
+    """setup -> run -> msd through PyCD's entry points on a full-PBC supercell: material_setup writes the
+    unit-cell rows, material_run picks them up by itself, runs the lattice-stencil kernel with incremental
+    updates (default refresh interval) and writes trajectories equal to the oracle's; material_msd equals
+    the oracle's analysis of the same trajectories."""
+    import json
+    import oracle as O
+    from pycd_b200 import material_msd, material_run, material_setup
+    from pycd_b200.material_setup import UNIT_ROWS_FILE
+    work, inp = _fast_path_workdir(tmp_path)
+    material_setup(inp, np.array([4, 4, 4]), np.array([1, 1, 1]), 1, 0, 1, 0, 0)
+    assert np.load(inp / UNIT_ROWS_FILE).shape == (30, 1920)
+    material_run(work)
+    info = json.load(open(work / 'Run.b200.json'))
+    assert info['p_layout'] == 'unit_rows' and info['stencil'] and info['refresh_interval'] == 256
+    assert info['step_kernel'] == 'kmc_step_warp_kernel<2,1,4>'
+    run, ref = _oracle_of_workdir(work, inp)
+    assert info['kmc_steps'] == int(ref['n_steps'].sum())
+    for i in range(16):
+        assert np.array_equal(np.load(work / f'traj{i + 1}' / 'unwrapped_traj.npy'), ref['unwrapped'][i])
+    material_msd(work)
+    sim = yaml.safe_load(open(work / 'simulation_parameters.yml'))
+    from pycd_b200 import constants
+    chk = O.msd_analysis(ref['unwrapped'], [64, 0], 51, run.time_interval, constants.AUTIME2NS,
+                         1 / constants.ANG2BOHR, 5, sim['temp'], sim['n_dim'])
+    msd = np.load(next(work.glob('MSD_Data_*.npy')))
+    assert np.allclose(msd, chk['msd_data'], rtol=1e-11, atol=1e-9)
+    log = next(work.glob('MSD_Analysis_*.log')).read_text()
+    assert f"{chk['diffusivity'][0]:.3e}" in log
+
+
+def _run_sharded(work, n_ranks, backend, shared_gpu):
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PYCD_DIST_BACKEND=backend)
+    if shared_gpu:
+        env['PYCD_B200_DEVICE'] = '0'
+    port = 29600 + os.getpid() % 300
+    code = ("import sys; sys.path.insert(0, %r); from pathlib import Path; from pycd_b200 import material_run; "
+            "material_run(Path(%r))" % (str(H.GOLD.parents[1]), str(work)))
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n_ranks}',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), '--no-python',
+                          sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.parametrize('mode', ['gloo_shared_gpu', 'nccl_two_gpus'])
+def test_material_run_under_torchrun_equals_single_process(tmp_path, mode):
+    """material_run launched as two ranks (trajectory blocks [0, 5) and [5, 10)): every traj<i>/ file, the
+    drift mobility and the step counts equal those of the one-process run of the same directory.  On a
+    one-GPU box both ranks share the GPU and gather over gloo; with two GPUs they use NCCL."""
+    import json
+    import torch
+    from pycd_b200 import material_run, material_setup
+    if mode == 'nccl_two_gpus' and torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    field = {'electric': {'active': 1, 'dir': [1, 0, 0], 'ld': 0, 'mag': 1.0e-4}}
+    work, inp = _fast_path_workdir(tmp_path, n_traj=10, size=(3, 3, 2), carriers=40, extra_b200={'refresh_interval': 64})
+    cfg = yaml.safe_load(open(work / 'simulation_parameters.yml'))
+    cfg['external_field'] = field
+    yaml.safe_dump(cfg, open(work / 'simulation_parameters.yml', 'w'))
+    material_setup(inp, np.array([3, 3, 2]), np.array([1, 1, 1]), 1, 0, 1, 0, 0)
+    material_run(work)
+    single = [np.load(work / f'traj{i + 1}' / 'unwrapped_traj.npy') for i in range(10)]
+    single_t = [np.load(work / f'traj{i + 1}' / 'time_data.npy') for i in range(10)]
+    single_mob = np.loadtxt(work / 'drift_mobility.dat', ndmin=2)
+    steps = json.load(open(work / 'Run.b200.json'))['kmc_steps']
+    for i in range(10):
+        shutil.rmtree(work / f'traj{i + 1}')
+    (work / 'Run.log').unlink()
+    (work / 'drift_mobility.dat').unlink()
+    _run_sharded(work, 2, 'gloo' if mode == 'gloo_shared_gpu' else 'nccl', mode == 'gloo_shared_gpu')
+    infos = [json.load(open(work / f'Run.b200.rank{r}.json')) for r in range(2)]
+    assert [i['trajectories'] for i in infos] == [[0, 5], [5, 10]]
+    assert sum(i['kmc_steps'] for i in infos) == steps
+    assert all(i['step_kernel'].startswith('kmc_step_warp_kernel') for i in infos)
+    if mode == 'nccl_two_gpus':
+        assert sorted(i['device'] for i in infos) == [0, 1]
+    for i in range(10):
+        assert np.array_equal(np.load(work / f'traj{i + 1}' / 'unwrapped_traj.npy'), single[i])
+        assert np.array_equal(np.load(work / f'traj{i + 1}' / 'time_data.npy'), single_t[i])
+    assert np.array_equal(np.loadtxt(work / 'drift_mobility.dat', ndmin=2), single_mob)
+    assert 'drift mobility' in (work / 'Run.log').read_text()
+
+
+def test_philox_run_honours_explicit_initial_sites(tmp_path):
+    """b200.rng: philox draws only the carriers the YAML did not place (initial_occupancy, core.py:2498-2510)."""
+    from pycd_b200 import material_run
+    from pycd_b200.tables import HopTables
+    ex = H.load_example('hematite')
+    sites = HopTables(ex.lattice, ex.supercell, ex.hop, 'electron').sites
+    pinned = [int(sites[3]), int(sites[17])]
+    work = _stage('hematite', tmp_path, {'species_count': [3, 0], 'n_traj': 2, 't_final': 2.0e-9,
+                                         'time_interval': 1.0e-9, 'initial_occupancy': {'electron': pinned},
+                                         'b200': {'rng': 'philox', 'chunk_steps': 64, 'refresh_interval': 1}})
+    material_run(work)
+    # with ~3 carriers x 3.2e9 hops/s, 2 ns hold ~20 hops: replay them backwards from the final positions is not
+    # needed -- the displacement of a carrier is a sum of hop vectors from its START site, so check the start
+    # sites through the oracle run of the same occupancy instead
+    import oracle as O
+    from pycd_b200 import kmc as K
+    from pycd_b200.material_run import PhiloxSampler
+    run = H.run_parameters(ex, dict(ex.sim, species_count=[3, 0], t_final=2.0e-9, time_interval=1.0e-9,
+                                    initial_occupancy={'electron': pinned}))
+    occ = np.array([run.initial_occupancy_from(PhiloxSampler(ex.sim['random_seed'], i)) for i in range(2)])
+    assert all(list(o[:2]) == pinned and o[2] not in pinned for o in occ)
+    ref = O.KmcOracle(run, ex.P, rng_mode=1, seed=ex.sim['random_seed'], stop_at_grid_end=True).ensemble(occ)
+    for i in range(2):
+        assert np.array_equal(np.load(work / f'traj{i + 1}' / 'unwrapped_traj.npy'), ref['unwrapped'][i])

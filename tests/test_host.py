@@ -209,7 +209,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(nat.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pycd_abi_version() == 2
+    assert lib.pycd_abi_version() == 3
     sass = subprocess.run(['cuobjdump', '-lelf', str(path)], capture_output=True, text=True).stdout
     assert 'sm_100a' in sass
 
