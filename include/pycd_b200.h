@@ -84,6 +84,12 @@ typedef struct {
     double k_cut;          /* yaml k_cut / ANG2BOHR, core.py:779-784 */
     double dielectric;     /* Material.dielectric_constant */
     int32_t k_max[3];      /* ceil(k_cut/|b_i|), core.py:1599 */
+    int32_t reserved;
+    int64_t plan_rows;     /* 0: the launch plan (tile shape, split-k factor) follows the rows of THIS call.
+                              > 0: plan as if plan_rows rows were evaluated.  Ranks that shard an array by row
+                              blocks pass the row count of the whole array, so that every block -- and the
+                              one-GPU evaluation of all rows -- sums the k vectors in the same order and the
+                              all-gathered array is bit-identical to the one-GPU array. */
 } pycd_ewald_desc;
 
 typedef struct {

@@ -88,7 +88,8 @@ class EwaldDesc(C.Structure):
     _fields_ = [('n_sites', C.c_int64), ('coords', C.c_void_p), ('cell', C.c_double * 9),
                 ('pbc', C.c_int32 * 3), ('recip', C.c_double * 9), ('volume', C.c_double),
                 ('alpha', C.c_double), ('r_cut', C.c_double), ('k_cut', C.c_double),
-                ('dielectric', C.c_double), ('k_max', C.c_int32 * 3)]
+                ('dielectric', C.c_double), ('k_max', C.c_int32 * 3), ('reserved', C.c_int32),
+                ('plan_rows', C.c_int64)]
 
 
 class EwaldStats(C.Structure):

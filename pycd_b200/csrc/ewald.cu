@@ -783,8 +783,12 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         PYCD_REQUIRE(desc->alpha > 0 && desc->volume > 0 && desc->dielectric > 0, "bad Ewald parameters");
         DeviceGuard g(ctx);
         const long long n_rows = row_end - row_begin;
+        // rows the launch plan is derived from: the call's own, or -- row blocks of a sharded array -- those
+        // of the whole array, so that every block sums the k vectors exactly like the one-GPU evaluation
+        PYCD_REQUIRE(desc->plan_rows >= 0, "bad plan_rows");
+        const long long plan_rows = desc->plan_rows > 0 ? std::max<long long>(desc->plan_rows, n_rows) : n_rows;
         // dense tile (64x128) for big row blocks, skinny tile (32x256) for the rows of one unit cell
-        const bool wide = n_rows > 64;
+        const bool wide = plan_rows > 64;
         // kernel variant (PYCD_EWALD_VARIANT, for A/B measurements): default = software-pipelined DMMA
         // kernel with 16-entry chunks (dense tile 64x128: 2 CTAs/SM; skinny tile 32x256: 1 CTA/SM with
         // 147 KB of double-buffered panels); "pipe16x1" / "pipe8" / "pipe8x1" = other chunk sizes / CTAs
@@ -824,10 +828,10 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
             PYCD_CUDA(cudaMemcpyAsync(kw.p, w.data(), w.size() * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
             const long long bm = wide ? (use_dmma ? 64 : 128) : 32, bn = wide ? 128 : 256;
-            const long long tiles = ((n_rows + bm - 1) / bm) * ((n + bn - 1) / bn);
+            const long long tiles = ((plan_rows + bm - 1) / bm) * ((n + bn - 1) / bn);
             // split-k so that the grid fills whole waves of the SMs (1 CTA/SM): among the
             // candidates pick the best-filled last wave, preferring fewer splits on ties
-            const long long ws_cap = std::max(1ll, (1ll << 30) / (n_rows * n * 8));
+            const long long ws_cap = std::max(1ll, (1ll << 30) / (plan_rows * n * 8));
             const long long ks_max = std::min({(long long)n_chunks, ws_cap, 32ll});
             const long long slots = (long long)ctx->n_sm * ((one_cta || ((pipe16 || pipe8) && !wide)) ? 1 : (use_dmma || !wide) ? 2 : 1);
             double best_fill = -1.0;

@@ -72,13 +72,16 @@ class EwaldParameters:
                 f'Fourier-space cutoff error: {fourier:.3e}\n\n']
 
 
-def ewald_rows(ctx, params, coords, row_begin, row_end, out=None):
+def ewald_rows(ctx, params, coords, row_begin, row_end, out=None, plan_rows=0):
     """P[row_begin:row_end, :] through pycd_ewald_rows.  coords / out: numpy arrays (host
-    path) or torch CUDA tensors / raw device addresses (resident path)."""
+    path) or torch CUDA tensors / raw device addresses (resident path).  plan_rows: row count of
+    the whole array when this call evaluates one block of a row-sharded array (every block then
+    uses the launch plan of the one-GPU evaluation and the gathered array is bit-identical to it)."""
     n = params.supercell.num_system_elements
     if out is None:
         out = np.empty((row_end - row_begin, n))
     desc = params.desc(coords)
+    desc.plan_rows = int(plan_rows)
     stats = nat.EwaldStats()
     nat.check(nat.lib().pycd_ewald_rows(ctx.handle, C.byref(desc), int(row_begin), int(row_end),
                                         nat.ptr(out), C.byref(stats)))

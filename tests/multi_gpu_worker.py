@@ -53,7 +53,7 @@ def main():
     for n_rows in (n, n - 7):   # equal and ragged row blocks
         full = torch.zeros((n_rows, n), dtype=torch.float64, device=dev)
         lo, hi = D.block(rank, world, n_rows)
-        EW.ewald_rows(ctx, ep, coords.data_ptr(), lo, hi, out=full[lo:hi].data_ptr())
+        EW.ewald_rows(ctx, ep, coords.data_ptr(), lo, hi, out=full[lo:hi].data_ptr(), plan_rows=n_rows)
         torch.cuda.synchronize()
         if backend == 'nccl':
             D.allgather_rows(full)

@@ -212,7 +212,11 @@ def test_drivers_reach_the_stencil_kernel_and_match_the_oracle(tmp_path):
     material_msd(work)
     sim = yaml.safe_load(open(work / 'simulation_parameters.yml'))
     from pycd_b200 import constants
-    chk = O.msd_analysis(ref['unwrapped'], [64, 0], 51, run.time_interval, constants.AUTIME2NS,
+    from pycd_b200.msd import MsdParameters
+    # step counts exactly as Analysis.__init__ truncates them (core.py:2968-2972: 50 lags here, not 51)
+    mp = MsdParameters(sim['n_dim'], [64, 0], 16, sim['t_final'], sim['time_interval'], sim['msd_t_final'],
+                       sim['trim_length'], sim['temp'])
+    chk = O.msd_analysis(ref['unwrapped'], [64, 0], mp.n_msd, run.time_interval, constants.AUTIME2NS,
                          1 / constants.ANG2BOHR, 5, sim['temp'], sim['n_dim'])
     msd = np.load(next(work.glob('MSD_Data_*.npy')))
     assert np.allclose(msd, chk['msd_data'], rtol=1e-11, atol=1e-9)

@@ -535,7 +535,7 @@ def test_stencil_kernel_bvo_shapes_match_oracle(ctx, case, refresh):
     assert np.array_equal(got['n_steps'], ref['n_steps'])
     assert np.array_equal(got['occupancy'], ref['occupancy'])
     assert np.array_equal(got['unwrapped'], ref['unwrapped'])
-    one = orc.trajectory(occ[5], traj_id=5, want_events=True)
+    one = orc.trajectory(occ[5], traj_id=5, cap_steps=steps, want_events=True)
     assert np.array_equal(res['events'][5, :steps], one['events'][:steps])
 
 
