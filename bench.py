@@ -49,10 +49,19 @@ def parse_args():
     ap.add_argument('--n-path', type=int, default=101, help='rows of the recorded time grid')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parity-budget', type=int, default=6_000_000,
+                    help='KMC steps the CPU oracle may spend re-running trajectories of the timed ensemble')
     ap.add_argument('--skip-msd', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='diagnostic: skip the L2 flush between iterations')
     ap.add_argument('--no-clocks', action='store_true', help='diagnostic: do not sample nvidia-smi clocks')
     ap.add_argument('--dense', action='store_true', help='step kernel gathers from the dense N x N array')
+    ap.add_argument('--config', type=int, default=3, choices=[2, 3, 4, 5],
+                    help='BASELINE.json configuration: 3 = the headline line (with bounded legs of 2, 4 and 5 '
+                         'attached as `configs`); 2 / 4 / 5 = that configuration alone at full size')
+    ap.add_argument('--skip-configs', action='store_true', help='headline line without the cfg 2 / 4 / 5 legs')
+    ap.add_argument('--sweep-traj', type=int, default=1024, help='--config 5: trajectories per condition (total)')
+    ap.add_argument('--sweep-common-grid', action='store_true',
+                    help='--config 5: one time grid for all conditions (hot conditions then take ~100x more steps)')
     return ap.parse_args()
 
 
@@ -169,6 +178,33 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def step_floor():
+    """Denominators of the step kernel's roofline from the committed microbenchmark of this device class
+    (tools/step_floor.cu -> profiles/r02_step_floor.json): L2 random 32-byte-sector gather peak and the
+    latency floor of one KMC step's dependency chain in the two-warp stencil kernel."""
+    f = ROOT / 'profiles' / 'r02_step_floor.json'
+    d = json.load(open(f)) if f.exists() else {}
+    g = lambda k, v: float(d.get(k, v))
+    dfma, dadd, dmma = g('lat_dfma_cycles', 8.4), g('lat_dadd_cycles', 8.2), g('lat_dmma_m8n8k4_operand_chain_cycles', 26.8)
+    lds, bar, redux = g('lat_lds_dependent_cycles', 34.0), g('lat_bar_sync_64_threads_cycles', 16.6), g('lat_redux_add_cycles', 44.2)
+    gather = g('lat_gather_3x32_sectors_1_warp_per_sm_cycles', 535.4)
+    terms = {
+        'rates: 22 dependent FP64 operations (Marcus argument, library exp sequence, pow correction, prefactor)': 22 * dfma,
+        'barrier + LDS + 3-level lane prefix': bar + lds + 3 * dadd,
+        'warp scan: 2 dependent DMMA + 2 FP64 operations': 2 * dmma + 2 * dfma,
+        'selection: threshold, compare, integer reduction (REDUX)': 2 * dfma + 30 + redux,
+        'table lookups of the selected process (LDS) + address arithmetic': lds + 15,
+        'three divergent 32-byte gathers per lane from the L2-resident table': gather,
+        'sum over carriers of the moved carrier\'s new terms: FMA + 4 chained DMMA + add + DMMA': dfma + 5 * dmma + dadd,
+        'exchange between the two warps: STS + barrier + LDS + 2 adds': bar + lds + 2 * dadd,
+        'patch of the cached sums': 2 * dfma,
+    }
+    return {'l2_gather_peak_gb_per_s': g('l2_gather_peak_gb_per_s', 9270.1),
+            'chain_cycles': float(sum(terms.values())), 'chain_terms': {k: round(v, 1) for k, v in terms.items()},
+            'source': 'measured (tools/step_floor.cu on a B200 of this pool, profiles/r02_step_floor.json)'
+                      if d else 'fallback constants (profiles/r02_step_floor.json missing)'}
+
+
 def profiled_traffic():
     """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
     f = ROOT / 'profiles' / 'kmc_step_traffic.json'
@@ -216,6 +252,25 @@ def ewald_cpu_baseline(sc, ep, n_sample=32):
                     'core) measures 20.4 ns per term (SURVEY 8a)'}
 
 
+def parity_check(run, P_host, occ, state, n_traj, steps, n_path, dt_grid, seed, traj_id0):
+    """The oracle (gather form, all host threads) on the first n_traj trajectories of the timed ensemble,
+    `steps` KMC steps each; compared with the state the GPU reached (read back after the timed region)."""
+    import oracle as O
+    orc = O.KmcOracle(run, P_host, literal=False, dt_grid=dt_grid, n_path=n_path, step_limit=steps,
+                      stop_at_grid_end=False, rng_mode=1, seed=seed)
+    t0 = time.perf_counter()
+    ref = orc.ensemble(occ[:n_traj], traj_id0=traj_id0, want_unwrapped=True, n_threads=host_cores())
+    dt = time.perf_counter() - t0
+    same = [bool(np.array_equal(ref['occupancy'][i], state['occupancy'][i]) and
+                 ref['n_steps'][i] == state['n_steps'][i] and
+                 np.array_equal(ref['unwrapped'][i], state['unwrapped'][i])) for i in range(n_traj)]
+    return {'checked': n_traj, 'equal': int(sum(same)), 'kmc_steps_per_trajectory': int(steps),
+            'what': 'final carrier sites, step counts and displacement grids of the timed ensemble (warm-up + '
+                    'timed launches) vs the CPU oracle (O(C) gather restatement of core.py:1989-2050, 2787-2861) '
+                    'run from the same initial sites and Philox keys',
+            'rate': ref['total_steps'] / dt, 'seconds': dt}
+
+
 def size_cpu_sample(run, P_host, occ, args, n_path, dt_grid, seed, literal):
     """Pick (#trajectories, steps) so that the sample costs about args.cpu_seconds."""
     cores = host_cores()
@@ -230,6 +285,7 @@ def size_cpu_sample(run, P_host, occ, args, n_path, dt_grid, seed, literal):
 # ---------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    rc = 0
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -285,12 +341,35 @@ def main():
     P = torch.empty((N, N), dtype=torch.float64, device=dev)
     coords = torch.from_numpy(np.ascontiguousarray(sc.coordinates)).to(dev)
     r0, r1 = (rank * N) // world, ((rank + 1) * N) // world
+    p_unit = torch.empty((sc.n_per_cell, N), dtype=torch.float64, device=dev)
+    # warm-up on the shipped 2x2x1 cell: the CUDA driver loads a kernel's code at its first launch, and both
+    # tile shapes + the expansion are used below
+    from pycd_b200 import constants as _c
+    from pycd_b200.lattice import Supercell as _Supercell
+    _sc0 = _Supercell(lat, [2, 2, 1], [1, 1, 1])
+    _ep0 = EW.EwaldParameters(_sc0, ep.alpha * _c.ANG2BOHR, ep.r_cut / _c.ANG2BOHR, ep.k_cut * _c.ANG2BOHR)
+    _pu0, _ = EW.ewald_rows(ctx, _ep0, np.ascontiguousarray(_sc0.coordinates), 0, _sc0.n_per_cell)
+    EW.ewald_expand(ctx, _sc0, _pu0, 0, _sc0.num_system_elements)
+    EW.ewald_rows(ctx, _ep0, np.ascontiguousarray(_sc0.coordinates), 0, _sc0.num_system_elements)
+    if dist:   # NCCL sets up its channels on the first collective of each kind: not part of the precompute
+        warm = torch.zeros(world * 1024, dtype=torch.float64, device=dev)
+        dist.all_reduce(warm)
+        dist.all_gather_into_tensor(warm, warm[:1024].clone())
+        del warm
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    p_unit = torch.empty((sc.n_per_cell, N), dtype=torch.float64, device=dev)
-    _, est = EW.ewald_rows(ctx, ep, coords.data_ptr(), 0, sc.n_per_cell, out=p_unit.data_ptr())
+    # rows of unit cell 0: every rank sums one contiguous part of the k list (part 0 also the real-space and
+    # self terms); one all-reduce of the n_per_cell x N rows (7.2 MB) completes them on every GPU
+    _, est = EW.ewald_rows(ctx, ep, coords.data_ptr(), 0, sc.n_per_cell, out=p_unit.data_ptr(),
+                           k_part=rank, k_parts=world)
+    t_reduce = 0.0
+    if dist:
+        tr = time.perf_counter()
+        dist.all_reduce(p_unit)
+        torch.cuda.synchronize()
+        t_reduce = time.perf_counter() - tr
     EW.ewald_expand(ctx, sc, p_unit.data_ptr(), r0, r1, out=P[r0:r1].data_ptr())
     expand_ms = ctx.last_kernel_ms(nat.KC_EWALD_EXPAND)
     torch.cuda.synchronize()
@@ -308,10 +387,12 @@ def main():
     ewald_seconds = time.perf_counter() - t0
     ewald_info = {'seconds': round(ewald_seconds, 4), 'k_eff': est['k_eff'], 'rows_direct': sc.n_per_cell,
                   'fourier_ms': round(est['fourier_ms'], 3), 'finish_ms': round(est['finish_ms'], 3),
-                  'expand_ms': round(expand_ms, 3), 'allgather_seconds': round(t_gather, 4),
-                  'fp64_tflops_fourier': round(4.0 * sc.n_per_cell * N * est['k_eff'] / (est['fourier_ms'] * 1e-3) / 1e12, 3)
+                  'expand_ms': round(expand_ms, 3), 'allreduce_unit_rows_seconds': round(t_reduce, 4),
+                  'allgather_seconds': round(t_gather, 4),
+                  'fp64_tflops_fourier': round(4.0 * sc.n_per_cell * N * est['k_eff'] / world / (est['fourier_ms'] * 1e-3) / 1e12, 3)
                   if est['fourier_ms'] > 0 else None,
-                  'method': 'rows of unit cell 0 on the GPU + translation expansion of the rank\'s row block'}
+                  'method': 'rows of unit cell 0 (k list split over the ranks + all-reduce), translation expansion '
+                            'of the rank\'s row block, all-gather of the dense array'}
 
     # ---- KMC system + ensemble -------------------------------------------------------
     if args.dense:
@@ -435,26 +516,50 @@ def main():
         mean = (part[0] / (world * nt)).cpu().numpy()
         msd_info = {'msd_ms': round(ctx.last_kernel_ms(nat.KC_MSD), 3), 'n_msd': n_msd,
                     'msd_last_A2': float(mean[-1])}
-    state = ens.read(unwrapped=False)
+    state = ens.read(unwrapped=True)
     near_tie = int(state['near_tie'].sum())
     ens.close()
 
+    # ---- the other BASELINE configurations as bounded legs (bench_configs.py) ---------------
+    configs = None
+    if not args.skip_configs and not args.dense:
+        import bench_configs as BC
+        e2e_ens.close()
+        configs = {}
+        # cfg 5: 8 conditions x 128 trajectories per GPU (weak: 1024 trajectories per GPU at every N)
+        configs['cfg5_sweep'] = BC.cfg5_sweep(ctx, dev, rank, world, dist, system, run,
+                                              traj_per_condition=128 * world)
+        configs['cfg2_bvo'] = BC.cfg2_bvo(ctx, dev, rank, world, dist)
+        p_keep = P if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+        if p_keep is None:
+            del P
+            torch.cuda.empty_cache()
+        configs['cfg4_ewald'] = BC.cfg4_ewald(ctx, dev, rank, world, dist)
+        if p_keep is not None:
+            P = p_keep
+
     # ---- CPU baseline on the host cores (rank 0, N=1 only) --------------------------------
     cpu = None
+    parity_in_bench = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         P_host = P.cpu().numpy()
         n_t, steps_c, rate1 = size_cpu_sample(run, P_host, occ, args, args.n_path, dt_grid, seed, True)
         rate, dt_c, tot, thr = cpu_reference_rate(run, P_host, occ, args, n_t, steps_c, args.n_path,
                                                   dt_grid, seed, literal=True)
-        n_g, steps_g, rate1g = size_cpu_sample(run, P_host, occ, args, args.n_path, dt_grid, seed, False)
-        rate_g, dt_g, tot_g, _ = cpu_reference_rate(run, P_host, occ, args, n_g, steps_g, args.n_path,
-                                                    dt_grid, seed, literal=False)
+        # the O(C) gather restatement re-runs trajectories 0..n_g-1 of the TIMED ensemble for every KMC step
+        # the GPU took (warm-up + timed launches) from the same sites and Philox keys: its final sites,
+        # step counts and displacement grids must equal what the GPU holds -- the bench run itself is checked
+        total_per_traj = int(state['n_steps'][0])
+        n_g = int(max(1, min(host_cores(), len(occ), args.parity_budget // max(total_per_traj, 1))))
+        parity = parity_check(run, P_host, occ, state, n_g, total_per_traj, args.n_path, dt_grid, seed, traj_id0)
+        rate_g, dt_g, steps_g = parity.pop('rate'), parity.pop('seconds'), total_per_traj
         cpu = {'value': rate, 'unit': 'KMC steps/s', 'cores': thr, 'kind': 'port',
                'sample': f'{n_t} trajectories x {steps_c} steps of the same ensemble, C port of the '
                          f'reference step loop (O(N) dot per process, core.py:2004-2008), '
                          f'{dt_c:.1f} s; 1 core: {rate1:.1f} steps/s',
                'gather_form_value': rate_g,
                'gather_form_sample': f'{n_g} trajectories x {steps_g} steps, O(C) gather restatement, {dt_g:.1f} s'}
+        parity_in_bench = parity
         del P_host
         ewald_info['cpu_baseline'] = ewald_cpu_baseline(sc, ep)
 
@@ -474,6 +579,32 @@ def main():
             touched = bstep if R_ == 1 else 8 * ((C_ - 1) * (2 + 2 * nn) + C_ * (nn + 1) + 2 * nn + 2) + bstep // R_
         k_ms = kern_ms / args.steps
         achieved = per_launch_bytes / (k_ms * 1e-3) / 1e9
+        floor = step_floor()
+        touched_gbs = touched * nt * S / (k_ms * 1e-3) / 1e9
+        sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+        cyc_step = k_ms * 1e-3 * sm_mhz * 1e6 / S
+        # The dominant kernel gathers 32-byte table entries that live in L2 (DRAM traffic per launch = one
+        # cold fetch of the tables, `traffic`): its bandwidth roofline is the L2 random-sector gather peak
+        # measured on this device (tools/step_floor.cu), and what actually bounds it at 3.5 trajectories per
+        # SM is the latency of one step's dependency chain (`latency`).
+        roofline = {'bound': 'l2', 'achieved': touched_gbs, 'peak': floor['l2_gather_peak_gb_per_s'],
+                    'unit': 'GB/s', 'frac': touched_gbs / floor['l2_gather_peak_gb_per_s'],
+                    'traffic': profiled_traffic(),
+                    'kernel': kernel_names.get(args.refresh), 'kernel_ms_per_launch': k_ms,
+                    'touched_bytes_per_kmc_step': touched, 'peak_source': floor['source'],
+                    'latency': {'cycles_per_kmc_step': cyc_step, 'floor_cycles': floor['chain_cycles'],
+                                'frac': floor['chain_cycles'] / cyc_step, 'floor_terms': floor['chain_terms'],
+                                'note': 'one KMC step is ONE dependency chain (rates -> scan -> selection -> '
+                                        'gathers -> reduction -> update); floor = sum of the measured '
+                                        'dependent-chain latencies of its unavoidable operations'},
+                    'algorithmic_ratio': {'bytes_per_kmc_step': bstep, 'algorithmic_bytes_per_launch': per_launch_bytes,
+                                          'achieved_gb_per_s': achieved, 'hbm_peak_gb_per_s': peak,
+                                          'ratio_to_hbm_peak': achieved / peak, 'hbm_peak_source': peak_src,
+                                          'note': 'SURVEY 8(d) algorithmic bytes of the STATELESS gather formulation '
+                                                  '(8*n_proc*(2C+6)+4*n_proc per step) x steps/s against the HBM '
+                                                  'peak: a ratio above 1 means the table form + incremental sums '
+                                                  'read fewer bytes than that formulation counts, not that HBM '
+                                                  'is exceeded'}}
         line = {
             'metric': 'KMC steps/s (all trajectories, box-wide)', 'value': value, 'unit': 'KMC steps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -496,32 +627,28 @@ def main():
                             'loads precomputed_array.npy once)'},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': profiled_traffic(),
-                         'kernel': kernel_names.get(args.refresh),
-                         'kernel_ms_per_launch': k_ms,
-                         'algorithmic_bytes_per_launch': per_launch_bytes,
-                         'bytes_per_kmc_step': bstep, 'peak_source': peak_src,
-                         'touched_bytes_per_kmc_step': touched,
-                         'touched_achieved': touched * nt * S / (k_ms * 1e-3) / 1e9,
-                         'note': 'algorithmic bytes are those of the STATELESS gather formulation (SURVEY 8d: '
-                                 '8*n_proc*(2C+6)+4*n_proc per KMC step); the kernel reads a precomputed '
-                                 'row-difference table (one 32-byte entry per carrier pair) and, with '
-                                 'refresh_interval>1, patches cached sums, so it touches touched_bytes_per_kmc_step '
-                                 'and frac exceeds 1; the step is bound by the latency of its dependency chain '
-                                 '(DESIGN.md 4.3), see stateless for the like-for-like figure'},
-            'cpu_baseline': cpu,
+            'roofline': roofline,
+            'cpu_baseline': cpu, 'parity_in_bench': parity_in_bench,
             'ewald': ewald_info, 'msd': msd_info, 'near_tie_fallbacks': near_tie,
+            'configs': configs,
         }
         if stateless:
             a1 = per_launch_bytes / (stateless['kernel_ms_per_launch'] * 1e-3) / 1e9
+            t1 = 8 * nn * C_ * C_ if ('warp' in (kernel_names.get(1) or '')) else bstep
+            l2_1 = t1 * nt * S / (stateless['kernel_ms_per_launch'] * 1e-3) / 1e9
             line['stateless'] = {'value': stateless['value'], 'kernel_ms_per_launch': stateless['kernel_ms_per_launch'],
-                                 'roofline_achieved': a1, 'roofline_frac': a1 / peak, 'kernel': kernel_names.get(1)}
+                                 'kernel': kernel_names.get(1), 'touched_bytes_per_kmc_step': t1,
+                                 'l2_gather_achieved_gb_per_s': l2_1,
+                                 'l2_gather_frac': l2_1 / floor['l2_gather_peak_gb_per_s'],
+                                 'algorithmic_gb_per_s': a1, 'algorithmic_ratio_to_hbm_peak': a1 / peak}
         print(json.dumps(line))
+        if parity_in_bench and parity_in_bench['equal'] != parity_in_bench['checked']:
+            print('bench.py: the timed ensemble differs from the CPU oracle', file=sys.stderr)
+            rc = 1
     if dist:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 # ---------------------------------------------------------------------------------------
@@ -584,6 +711,64 @@ def reference_timed(args, run, P_host, N):
     return 0
 
 
+def single_config(args):
+    """--config 2 / 4 / 5: that BASELINE configuration alone, one JSON line."""
+    import torch
+    import bench_configs as BC
+    from pycd_b200 import _native as nat
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    if nat.needs_build():
+        nat.build()
+    ctx = nat.default_context(local_rank)
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
+    l0 = ctx.launch_count()
+    if args.config == 2:
+        res = BC.cfg2_bvo(ctx, dev, rank, world, dist, traj_per_gpu=args.traj_per_gpu, launches=max(args.steps, 1))
+        metric, hib, scaling = 'KMC steps/s (all trajectories, box-wide)', True, 'weak'
+    elif args.config == 4:
+        res = BC.cfg4_ewald(ctx, dev, rank, world, dist)
+        metric, hib, scaling = 'Ewald precompute s', False, 'strong'
+    else:
+        from pycd_b200 import ewald as EW, kmc as K
+        lat, sc, run, ep = build_problem(args)
+        p_unit, _ = EW.ewald_rows(ctx, ep, np.ascontiguousarray(sc.coordinates), 0, sc.n_per_cell)
+        system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+        res = BC.cfg5_sweep(ctx, dev, rank, world, dist, system, run, traj_per_condition=args.sweep_traj,
+                            common_grid=args.sweep_common_grid)
+        system.close()
+        metric, hib, scaling = 'KMC steps/s (all trajectories, box-wide)', True, 'strong'
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        line = {'metric': metric, 'value': res['value'], 'unit': res['unit'], 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'higher_is_better': hib, 'scaling': scaling, 'vs_baseline': None,
+                'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': res['workload'], 'baseline_config': args.config},
+                'gpu_launches': int(ctx.launch_count() - l0), 'clocks': clocks, 'detail': res}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def reference_arm_small(args):
     """No GPU visible (build container): time the port on the shipped 2x2x1 example."""
     import helpers as H
@@ -599,4 +784,6 @@ if __name__ == '__main__':
         if int(os.environ.get('RANK', '0')) != 0:
             sys.exit(0)
         sys.exit(reference_arm(a) if torch.cuda.is_available() else reference_arm_small(a))
+    if a.config != 3:
+        sys.exit(single_config(a))
     sys.exit(main())

@@ -84,12 +84,17 @@ typedef struct {
     double k_cut;          /* yaml k_cut / ANG2BOHR, core.py:779-784 */
     double dielectric;     /* Material.dielectric_constant */
     int32_t k_max[3];      /* ceil(k_cut/|b_i|), core.py:1599 */
-    int32_t reserved;
+    int32_t k_part;        /* with k_parts > 1 (the unit-cell rows sharded over GPUs by k range): this call sums
+                              only part k_part of k_parts contiguous parts of the k list; part 0 also carries
+                              the real-space and self terms, so the SUM of the parts' outputs (one all-reduce)
+                              is P.  k_parts <= 1: everything */
     int64_t plan_rows;     /* 0: the launch plan (tile shape, split-k factor) follows the rows of THIS call.
                               > 0: plan as if plan_rows rows were evaluated.  Ranks that shard an array by row
                               blocks pass the row count of the whole array, so that every block -- and the
                               one-GPU evaluation of all rows -- sums the k vectors in the same order and the
                               all-gathered array is bit-identical to the one-GPU array. */
+    int32_t k_parts;
+    int32_t reserved;
 } pycd_ewald_desc;
 
 typedef struct {
@@ -183,6 +188,9 @@ typedef struct {
     const double *dopant_dq;   /* (n_traj, D): dopant charge minus the undoped lattice charge of the site
                                   (charge_config, core.py:2553-2557); the device adds
                                   sum_d dq_d P[s, d] to the trajectory's lattice potential */
+    const double *dt_grid_traj;/* NULL or (n_traj): per-trajectory time_interval in place of dt_grid (a sweep
+                                  flattened into one ensemble: every condition keeps the time grid its own
+                                  simulation_parameters.yml would give it) */
 } pycd_kmc_ensemble_desc;
 
 int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ensemble_desc *desc,

@@ -88,8 +88,8 @@ class EwaldDesc(C.Structure):
     _fields_ = [('n_sites', C.c_int64), ('coords', C.c_void_p), ('cell', C.c_double * 9),
                 ('pbc', C.c_int32 * 3), ('recip', C.c_double * 9), ('volume', C.c_double),
                 ('alpha', C.c_double), ('r_cut', C.c_double), ('k_cut', C.c_double),
-                ('dielectric', C.c_double), ('k_max', C.c_int32 * 3), ('reserved', C.c_int32),
-                ('plan_rows', C.c_int64)]
+                ('dielectric', C.c_double), ('k_max', C.c_int32 * 3), ('k_part', C.c_int32),
+                ('plan_rows', C.c_int64), ('k_parts', C.c_int32), ('reserved', C.c_int32)]
 
 
 class EwaldStats(C.Structure):
@@ -115,7 +115,7 @@ class KmcEnsembleDesc(C.Structure):
                 ('kT_traj', C.c_void_p), ('field_traj', C.c_void_p),
                 ('record_unwrapped', C.c_int32), ('energy0', C.c_void_p),
                 ('e_rel_traj', C.c_void_p), ('n_dopant_max', C.c_int32),
-                ('dopant_site', C.c_void_p), ('dopant_dq', C.c_void_p)]
+                ('dopant_site', C.c_void_p), ('dopant_dq', C.c_void_p), ('dt_grid_traj', C.c_void_p)]
 
 
 _lib = None

@@ -605,6 +605,7 @@ struct FinishParams {
     double cell[9], cellinv[9];
     int pbc[3];
     double sqrt_alpha, r_cut, eps, self_term;
+    int fourier_only;   // k-range shards other than part 0: reciprocal-space partial sum only
 };
 
 // Real-space term with the reference's 27-image minimum-image search
@@ -621,6 +622,10 @@ ewald_finish_kernel(const double *__restrict__ coords, long long n_sites, long l
         const long long il = idx / n_sites, j = idx - il * n_sites, i = row0 + il;
         double f = 0.0;
         for (int s = 0; s < k_split; ++s) f += partials[(long long)s * total + idx];
+        if (fp.fourier_only) {
+            out[idx] = (f * 2) / fp.eps;
+            continue;
+        }
         const double dx = coords[3 * j] - coords[3 * i], dy = coords[3 * j + 1] - coords[3 * i + 1],
                      dz = coords[3 * j + 2] - coords[3 * i + 2];
         double fr[3];
@@ -805,7 +810,13 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         std::vector<KEntry> ent;
         std::vector<double> w;
         const int64_t k_eff = build_k_list(*desc, KC, ent, w);
-        const int n_chunks = (int)(ent.size() / KC);
+        const int n_chunks_all = (int)(ent.size() / KC);
+        // k-range shard: part k_part of k_parts contiguous parts of the (padded) k list
+        const int k_parts = desc->k_parts > 1 ? desc->k_parts : 1;
+        PYCD_REQUIRE(desc->k_part >= 0 && desc->k_part < k_parts, "bad k_part");
+        const int chunk_lo = (int)(((long long)n_chunks_all * desc->k_part) / k_parts);
+        const int chunk_hi = (int)(((long long)n_chunks_all * (desc->k_part + 1)) / k_parts);
+        const int n_chunks = chunk_hi - chunk_lo;
 
         InBuf<double> coords;
         coords.bind(desc->coords, (size_t)n * 3, ctx->stream);
@@ -821,11 +832,11 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
 
         int k_split = 1;
         if (n_chunks > 0) {
-            kent.alloc(ent.size());
-            kw.alloc(w.size());
-            PYCD_CUDA(cudaMemcpyAsync(kent.p, ent.data(), ent.size() * sizeof(KEntry),
+            kent.alloc((size_t)n_chunks * KC);
+            kw.alloc((size_t)n_chunks * KC);
+            PYCD_CUDA(cudaMemcpyAsync(kent.p, ent.data() + (size_t)chunk_lo * KC, (size_t)n_chunks * KC * sizeof(KEntry),
                                       cudaMemcpyHostToDevice, ctx->stream));
-            PYCD_CUDA(cudaMemcpyAsync(kw.p, w.data(), w.size() * sizeof(double),
+            PYCD_CUDA(cudaMemcpyAsync(kw.p, w.data() + (size_t)chunk_lo * KC, (size_t)n_chunks * KC * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
             const long long bm = wide ? (use_dmma ? 64 : 128) : 32, bn = wide ? 128 : 256;
             const long long tiles = ((plan_rows + bm - 1) / bm) * ((n + bn - 1) / bn);
@@ -890,6 +901,7 @@ extern "C" int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64
         fp.r_cut = desc->r_cut;
         fp.eps = desc->dielectric;
         fp.self_term = -sqrt(desc->alpha / M_PI) / desc->dielectric;  // core.py:1659
+        fp.fourier_only = desc->k_part > 0 && k_parts > 1;
         KernelTimer tr(ctx, KC_EWALD_FINISH);
         const long long total = n_rows * n;
         const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->n_sm * 16);

@@ -499,7 +499,7 @@ kmc_step_kernel(SysDev S_in, EnsDev E, AdvanceArgs A)
         // ---- thread 0: time advance, grid bookkeeping, hop, core.py:2802-2830, 2844-2861 ----
         if (tid == 0) {
             t += nlog_u2 / ktot;
-            const long long end = (long long)(t / E.dt_grid);
+            const long long end = (long long)(t / (E.dt_grid_traj ? E.dt_grid_traj[traj] : E.dt_grid));
             const long long start_before = start;
             StepCtl ctl;
             ctl.r0 = 0; ctl.r1 = 0; ctl.fin = 0; ctl.pad = 0;
@@ -983,7 +983,7 @@ kmc_step_carrier_kernel(SysDev S, EnsDev E, AdvanceArgs A)
         // ---- thread 0: time advance, grid bookkeeping, hop, core.py:2802-2830, 2844-2861 ----
         if (tid == 0) {
             t += nlog_u2 / ktot;
-            const long long end = (long long)(t / E.dt_grid);
+            const long long end = (long long)(t / (E.dt_grid_traj ? E.dt_grid_traj[traj] : E.dt_grid));
             const long long start_before = start;
             StepCtl ctl;
             ctl.r0 = 0; ctl.r1 = 0; ctl.fin = 0; ctl.pad = 0;
@@ -1247,7 +1247,7 @@ struct pycd_kmc_ensemble {
     pycd_kmc_system *sys = nullptr;
     EnsDev dev{};
     DevBuf<int> occ, done;
-    DevBuf<double> t, disp, row, drift, rates, unwrapped, kT_traj, field_traj, energy, energy_grid, dg0_grid;
+    DevBuf<double> t, disp, row, drift, rates, unwrapped, kT_traj, field_traj, dt_grid_traj, energy, energy_grid, dg0_grid;
     DevBuf<double> e_rel_traj, v_lat_traj;   // doped ensembles only
     std::vector<double> energy0;
     DevBuf<long long> start_idx, n_steps, near_tie, clamped;
@@ -1623,6 +1623,14 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
                 ens->kT_traj.alloc(nt);
                 PYCD_CUDA(cudaMemcpyAsync(ens->kT_traj.p, d->kT_traj, sizeof(double) * nt, cudaMemcpyDefault, s));
             }
+            if (d->dt_grid_traj) {
+                std::vector<double> dtg((size_t)nt);
+                PYCD_CUDA(cudaMemcpy(dtg.data(), d->dt_grid_traj, sizeof(double) * nt, cudaMemcpyDefault));
+                for (double v : dtg) PYCD_REQUIRE(v > 0, "bad per-trajectory time grid");
+                ens->dt_grid_traj.alloc(nt);
+                PYCD_CUDA(cudaMemcpyAsync(ens->dt_grid_traj.p, dtg.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, s));
+                PYCD_CUDA(cudaStreamSynchronize(s));
+            }
             if (d->field_traj) {
                 ens->field_traj.alloc((size_t)nt * 3);
                 PYCD_CUDA(cudaMemcpyAsync(ens->field_traj.p, d->field_traj, sizeof(double) * nt * 3, cudaMemcpyDefault, s));
@@ -1665,7 +1673,7 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
             e.occ = ens->occ.p; e.t = ens->t.p; e.start_idx = ens->start_idx.p; e.done = ens->done.p;
             e.disp = ens->disp.p; e.row = ens->row.p; e.n_steps = ens->n_steps.p;
             e.near_tie = ens->near_tie.p; e.clamped = ens->clamped.p; e.drift = ens->drift.p;
-            e.rates = ens->rates.p; e.kT_traj = ens->kT_traj.p; e.field_traj = ens->field_traj.p;
+            e.rates = ens->rates.p; e.kT_traj = ens->kT_traj.p; e.field_traj = ens->field_traj.p; e.dt_grid_traj = ens->dt_grid_traj.p;
             e.unwrapped = ens->unwrapped.p; e.dt_grid = d->dt_grid; e.n_path = d->n_path;
             e.step_limit = d->step_limit; e.stop_at_grid_end = d->stop_at_grid_end;
             e.rng_mode = d->rng_mode; e.seed = d->seed; e.refresh_interval = d->refresh_interval;

@@ -47,6 +47,7 @@ struct EnsDev {
     double *rates;         // [n_traj][n_proc]
     const double *kT_traj;
     const double *field_traj;
+    const double *dt_grid_traj; // NULL or [n_traj]: per-trajectory time_interval (sweeps: one grid per condition)
     const double *e_rel_traj;  // NULL or [n_traj][N]: a doped trajectory's site energies (core.py:2750-2764)
     const double *v_lat_traj;  // NULL or [n_traj][N]: its lattice potential, dopant charges included
     double *unwrapped;     // [n_traj][n_path][3C] or NULL

@@ -72,16 +72,19 @@ class EwaldParameters:
                 f'Fourier-space cutoff error: {fourier:.3e}\n\n']
 
 
-def ewald_rows(ctx, params, coords, row_begin, row_end, out=None, plan_rows=0):
+def ewald_rows(ctx, params, coords, row_begin, row_end, out=None, plan_rows=0, k_part=0, k_parts=1):
     """P[row_begin:row_end, :] through pycd_ewald_rows.  coords / out: numpy arrays (host
     path) or torch CUDA tensors / raw device addresses (resident path).  plan_rows: row count of
     the whole array when this call evaluates one block of a row-sharded array (every block then
-    uses the launch plan of the one-GPU evaluation and the gathered array is bit-identical to it)."""
+    uses the launch plan of the one-GPU evaluation and the gathered array is bit-identical to it).
+    k_part / k_parts: sum only one contiguous part of the k list (part 0 carries the real-space and self
+    terms too): the unit-cell rows sharded over GPUs by k range, completed by ONE all-reduce (sum)."""
     n = params.supercell.num_system_elements
     if out is None:
         out = np.empty((row_end - row_begin, n))
     desc = params.desc(coords)
     desc.plan_rows = int(plan_rows)
+    desc.k_part, desc.k_parts = int(k_part), int(k_parts)
     stats = nat.EwaldStats()
     nat.check(nat.lib().pycd_ewald_rows(ctx.handle, C.byref(desc), int(row_begin), int(row_end),
                                         nat.ptr(out), C.byref(stats)))

@@ -91,7 +91,9 @@ class RunParameters:
                                      self.lattice.species_charge_list[self.species_charge_type]))
         ewald_neut = -(np.pi * system_charge ** 2 / (2 * sc.system_volume * alpha))
         q = np.array(self.q_lat if q_lat is None else q_lat, dtype=np.float64, copy=True)
-        np.add.at(q, np.asarray(occupancy, dtype=int), self.q_carrier)
+        # core.py:2561-2564: `charge_list[sites] += q_c` is a fancy-index assignment, so a site that holds
+        # several carriers (no site exclusion) is counted ONCE; replicated literally
+        q[np.asarray(occupancy, dtype=int)] += self.q_carrier
         return ewald_neut + float(q @ (P @ q))
 
     # -- initial state -----------------------------------------------------------------
@@ -126,10 +128,22 @@ def write_initial_rnd_states(dst_path, n_traj, random_seed, only=None):
             pickle.dump(rng.getstate(), fh)
 
 
+class _PlainUnpickler(pickle.Unpickler):
+    """initial_rnd_state.dump holds random.getstate(): a tuple of ints / a tuple of ints / None -- no
+    class may be instantiated while loading it."""
+
+    def find_class(self, module, name):
+        raise pickle.UnpicklingError(f'initial_rnd_state.dump must not reference {module}.{name}')
+
+
 def load_rnd_state(path):
     rng = _random.Random()
     with open(path, 'rb') as fh:
-        rng.setstate(pickle.load(fh))
+        state = _PlainUnpickler(fh).load()
+    if not (isinstance(state, tuple) and len(state) == 3 and isinstance(state[1], tuple)
+            and all(isinstance(v, int) for v in state[1])):
+        raise ValueError(f'{path}: not a random.getstate() dump')
+    rng.setstate(state)
     return rng
 
 
@@ -233,7 +247,7 @@ class KmcEnsemble:
     def __init__(self, system, occupancy0, dt_grid=None, n_path=None, step_limit=0,
                  stop_at_grid_end=True, rng_mode=nat.RNG_REPLAY, seed=0, traj_id0=0,
                  refresh_interval=1, kT_traj=None, field_traj=None, record_unwrapped=True, energy0=None,
-                 doping=None):
+                 doping=None, dt_grid_traj=None):
         """doping: None or one doping.TrajectoryDoping per trajectory (core.py:2723-2776): the
         trajectory's shifted site energies and the charges its dopant sites carry."""
         run = system.run
@@ -268,6 +282,11 @@ class KmcEnsemble:
             assert field_traj.shape == (self.n_traj, 3)
             d.field_traj = nat.ptr(field_traj)
             keep.append(field_traj)
+        if dt_grid_traj is not None:   # one time grid per trajectory (sweeps: one per condition)
+            dt_grid_traj = np.ascontiguousarray(dt_grid_traj, dtype=np.float64)
+            assert dt_grid_traj.shape == (self.n_traj,) and np.all(dt_grid_traj > 0)
+            d.dt_grid_traj = nat.ptr(dt_grid_traj)
+            keep.append(dt_grid_traj)
         self.has_energy = energy0 is not None
         if energy0 is not None:
             energy0 = np.ascontiguousarray(energy0, dtype=np.float64)

@@ -31,6 +31,8 @@ class MsdParameters:
         self.n_msd = int(self.msd_t_final / self.time_interval) + 1
         if self.n_msd > self.n_path:
             raise ValueError('msd_t_final exceeds t_final (the reference silently mis-indexes here)')
+        if self.trim_length < 1:   # msd[trim:-trim] is EMPTY for trim = 0 (the reference's linregress raises on it)
+            raise ValueError('trim_length must be >= 1: rows [trim:-trim] feed the diffusivity fit (core.py:3052-3058)')
         if 2 * self.trim_length >= self.n_msd:
             raise ValueError('trim_length leaves no points for the diffusivity fit')
 

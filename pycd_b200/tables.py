@@ -29,10 +29,21 @@ ReturnValues.__qualname__ = 'ReturnValues'
 
 
 class _HopListUnpickler(pickle.Unpickler):
+    """hop_neighbor_list.npy is a pickled dict of ReturnValues objects holding numpy arrays
+    (core.py:565-569, 663): only those globals are resolved; anything else in the file is refused
+    instead of being imported and called."""
+    _NUMPY = {('numpy.core.multiarray', '_reconstruct'), ('numpy._core.multiarray', '_reconstruct'),
+              ('numpy.core.multiarray', 'scalar'), ('numpy._core.multiarray', 'scalar'),
+              ('numpy', 'ndarray'), ('numpy', 'dtype'),
+              ('numpy.core.numeric', '_frombuffer'), ('numpy._core.numeric', '_frombuffer'),
+              ('_codecs', 'encode'), ('__builtin__', 'bytes'), ('builtins', 'bytes')}   # byte strings of protocol-2 pickles
+
     def find_class(self, module, name):
         if name == 'ReturnValues':
             return ReturnValues
-        return super().find_class(module, name)
+        if (module, name) in self._NUMPY:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f'hop_neighbor_list.npy must not reference {module}.{name}')
 
 
 def load_hop_neighbor_list(path):

@@ -66,6 +66,21 @@ def main():
         torch.cuda.synchronize()
         assert torch.equal(full, single), f'rank {rank}: gathered Ewald array differs from the one-GPU array'
 
+    # 1b. rows of unit cell 0 sharded by k range: every rank sums one part of the k list, one all-reduce
+    part = torch.empty((sc.n_per_cell, n), dtype=torch.float64, device=dev)
+    EW.ewald_rows(ctx, ep, coords.data_ptr(), 0, sc.n_per_cell, out=part.data_ptr(), k_part=rank, k_parts=world)
+    torch.cuda.synchronize()
+    if backend == 'nccl':
+        dist.all_reduce(part)
+    else:
+        host = part.cpu()
+        dist.all_reduce(host)
+        part = host.to(dev)
+    one = torch.empty((sc.n_per_cell, n), dtype=torch.float64, device=dev)
+    EW.ewald_rows(ctx, ep, coords.data_ptr(), 0, sc.n_per_cell, out=one.data_ptr())
+    torch.cuda.synchronize()
+    assert float((part - one).abs().max()) <= 1e-13 * float(one.abs().max()), 'k-range shards do not add up'
+
     # 2. KMC: trajectories in contiguous blocks, Philox keyed by the global id; sharded == unsharded
     p_unit = torch.empty((sc.n_per_cell, n), dtype=torch.float64, device=dev)
     EW.ewald_rows(ctx, ep, coords.data_ptr(), 0, sc.n_per_cell, out=p_unit.data_ptr())
