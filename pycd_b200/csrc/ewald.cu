@@ -657,25 +657,36 @@ ewald_finish_kernel(const double *__restrict__ coords, long long n_sites, long l
     }
 }
 
-// P[i,j] = Pu[b_i][(cell_j - cell_i mod size)*nb + b_j]
+// P[i,j] = Pu[b_i][(cell_j - cell_i mod size)*nb + b_j].  HBM-write bound (8 N bytes per row): one CTA per
+// (row i, x index of the target cell); for every y the sz*nb elements of the z column are contiguous in the
+// output AND in the source row up to one wrap (source offset = target offset - z_i*nb, + sz*nb if negative),
+// so an element costs a compare, two adds, a load from the L2-resident unit-cell rows and a coalesced store --
+// no division per element (the first version spent its time in five 64-bit divisions per element).
 __global__ void __launch_bounds__(256)
 ewald_expand_kernel(const double *__restrict__ pu, int nb, int sx, int sy, int sz,
                     long long n_sites, long long row0, long long n_rows, double *__restrict__ out)
 {
-    const long long total = n_rows * n_sites;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long il = idx / n_sites;
-        const int j = (int)(idx - il * n_sites), i = (int)(row0 + il);
-        const int ci = i / nb, bi = i - ci * nb, cj = j / nb, bj = j - cj * nb;
+    const int xj = blockIdx.x;
+    for (long long il = blockIdx.y; il < n_rows; il += gridDim.y) {
+        const int i = (int)(row0 + il);
+        const int ci = i / nb, bi = i - ci * nb;
         const int zi = ci % sz, yi = (ci / sz) % sy, xi = ci / (sz * sy);
-        const int zj = cj % sz, yj = (cj / sz) % sy, xj = cj / (sz * sy);
-        int ddx = xj - xi, ddy = yj - yi, ddz = zj - zi;
+        int ddx = xj - xi;
         ddx += ddx < 0 ? sx : 0;
-        ddy += ddy < 0 ? sy : 0;
-        ddz += ddz < 0 ? sz : 0;
-        const int dc = (ddx * sy + ddy) * sz + ddz;
-        out[idx] = pu[(long long)bi * n_sites + (long long)dc * nb + bj];
+        const int szn = sz * nb, shift = zi * nb;
+        const double *src_row = pu + (long long)bi * n_sites;
+        double *dst_row = out + il * n_sites + (long long)xj * sy * szn;
+        for (int yj = threadIdx.y; yj < sy; yj += blockDim.y) {
+            int ddy = yj - yi;
+            ddy += ddy < 0 ? sy : 0;
+            const double *src = src_row + (long long)(ddx * sy + ddy) * szn;
+            double *dst = dst_row + (long long)yj * szn;
+            for (int e = threadIdx.x; e < szn; e += blockDim.x) {
+                int se = e - shift;
+                se += se < 0 ? szn : 0;
+                dst[e] = __ldg(src + se);
+            }
+        }
     }
 }
 
@@ -941,9 +952,12 @@ extern "C" int pycd_ewald_expand(pycd_ctx *ctx, const double *p_unit, int32_t n_
         OutBuf<double> o;
         o.bind(out, (size_t)n_rows * n);
         KernelTimer t(ctx, KC_EWALD_EXPAND);
-        const long long total = n_rows * n;
-        const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->n_sm * 32);
-        ewald_expand_kernel<<<blocks, 256, 0, ctx->stream>>>(pu.p, n_basis, size[0], size[1], size[2], n,
+        // threads: x over the z column of a target cell row (sz*nb contiguous elements), y over the y index
+        const int szn = size[2] * n_basis;
+        const unsigned tx = szn >= 256 ? 256u : (szn > 128 ? 128u : (szn > 64 ? 64u : 32u));
+        const dim3 block(tx, 256u / tx);
+        const dim3 grid((unsigned)size[0], (unsigned)std::min<long long>(n_rows, 65535));
+        ewald_expand_kernel<<<grid, block, 0, ctx->stream>>>(pu.p, n_basis, size[0], size[1], size[2], n,
                                                              row_begin, n_rows, o.dev());
         check_launch(ctx, "ewald_expand_kernel");
         t.stop(1);

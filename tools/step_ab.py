@@ -18,19 +18,13 @@ OUT = ROOT / 'scratch' / 'ab'
 
 VARIANTS = {
     'default': [],
+    'dummy_store_off': ['-DPYCD_DUMMY_STORE=0'],
     'owner_late': ['-DPYCD_OWNER_EARLY=0'],
-    'patch_late': ['-DPYCD_PATCH_EARLY=0'],
+    'patch_early': ['-DPYCD_PATCH_EARLY=1'],
+    'one_chain': ['-DPYCD_SUM_CHAINS=1'],
     'exp_library': ['-DPYCD_EXP_TABLE=0'],
     'owner_loads_last': ['-DPYCD_OWNER_LOADS_FIRST=0'],
-    'all_off': ['-DPYCD_OWNER_EARLY=0', '-DPYCD_PATCH_EARLY=0', '-DPYCD_EXP_TABLE=0', '-DPYCD_OWNER_LOADS_FIRST=0'],
-    'shuffle_scan_and_sums': ['-DPYCD_SCAN_DMMA=0', '-DPYCD_SUM_DMMA=0'],
     'h1_select': ['-DPYCD_H1_PRED=0'],
-    'one_chain': ['-DPYCD_SUM_CHAINS=1'],
-    'late_late': ['-DPYCD_OWNER_EARLY=0', '-DPYCD_PATCH_EARLY=0'],
-    'late_late_h1sel': ['-DPYCD_OWNER_EARLY=0', '-DPYCD_PATCH_EARLY=0', '-DPYCD_H1_PRED=0'],
-    'late_late_h1sel_1chain': ['-DPYCD_OWNER_EARLY=0', '-DPYCD_PATCH_EARLY=0', '-DPYCD_H1_PRED=0', '-DPYCD_SUM_CHAINS=1'],
-    'late_late_h1sel_1chain_libexp_loadslast': ['-DPYCD_OWNER_EARLY=0', '-DPYCD_PATCH_EARLY=0', '-DPYCD_H1_PRED=0',
-                                                '-DPYCD_SUM_CHAINS=1', '-DPYCD_EXP_TABLE=0', '-DPYCD_OWNER_LOADS_FIRST=0'],
 }
 # a header from the history compiled against today's kmc_types.cuh: HEADER@<git rev>
 HISTORY = {'committed_dc5ad1f': 'dc5ad1f'}
