@@ -3,11 +3,16 @@ material_setup.py:21-34).  Parsed with yaml.safe_load (the reference's bare yaml
 needs PyYAML < 6).  New, optional knobs of this implementation live under the `b200:`
 key of simulation_parameters.yml so that existing files load unchanged:
 
-    b200:
+    b200:                      # simulation_parameters.yml (material_run)
       rng: replay | philox     # default replay = the reference's MT19937 streams
-      refresh_interval: 1      # 1 = stateless rate evaluation (reference formulation)
+      refresh_interval: 256    # philox mode; 1 = stateless rate evaluation (the reference formulation,
+                               # always used in replay mode)
       chunk_steps: 32768       # KMC steps per kernel launch
-      ewald_symmetric: auto    # auto | true | false
+      p_layout: auto           # auto | unit_rows | dense: which Ewald table the step kernel reads
+
+    b200:                      # sys_config.yml (material_setup)
+      ewald_symmetric: auto    # auto | true | false: rows of unit cell 0 + translation, or all rows directly
+      dense_limit_gb: 4        # the dense N x N file is skipped above this size when the unit rows exist
 """
 from types import SimpleNamespace
 

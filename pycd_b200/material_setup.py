@@ -46,6 +46,15 @@ def material_setup(input_directory_path, system_size, pbc, generate_hop_neighbor
         opts = getattr(params, 'b200', None) or {}
         n = supercell.num_system_elements
         symmetric = ew.can_use_translation_symmetry(supercell)
+        # b200.ewald_symmetric (sys_config.yml): auto = use translation symmetry when valid; false = evaluate
+        # all N rows directly (the reference's formulation; cfg 4); true = insist on it
+        want_sym = opts.get('ewald_symmetric', 'auto')
+        if want_sym not in ('auto', True, False, 'true', 'false'):
+            raise ValueError(f"b200.ewald_symmetric must be auto, true or false, not {want_sym!r}")
+        if want_sym in (True, 'true') and not symmetric:
+            raise ValueError('b200.ewald_symmetric: true needs pbc = [1, 1, 1] and more than one cell')
+        if want_sym in (False, 'false'):
+            symmetric = False
         # Full PBC: the rows of unit cell 0 determine the whole array.  They are written
         # next to the reference's file; material_run prefers them (L2-resident table, stencil kernel).
         # The dense N x N file stays the exchange format with the reference and is written unless it would

@@ -115,6 +115,39 @@ def test_translation_path_equals_all_pairs():
         assert np.abs(a['Fe:Fe'][0][hi].vector - b['Fe:Fe'][0][hi].vector).max() < 1e-12
 
 
+def test_full_size_tables_match_brute_force_on_sampled_sites():
+    """BASELINE config 3 (Hematite 10x10x10, N = 30 000): the tables the oracle AND the CUDA path read at
+    full size come from the translation path; here rows of sampled Fe sites are rebuilt independently --
+    literal 27-image minimum image of the site against every Fe site (core.py:304-361) and the
+    reference's selection rule lo < r <= hi in ascending site index (core.py:529-533, 617-640)."""
+    ex = H.load_example('hematite')
+    sc = Supercell(ex.lattice, [10, 10, 10], [1, 1, 1])
+    assert sc.num_system_elements == 30000
+    tabs = sc.hop_neighbor_tables()['Fe:Fe'][0]
+    lat = ex.lattice
+    ti = lat.element_types.index('Fe')
+    sites = sc.element_sites(ti)
+    rng = np.random.default_rng(5)
+    picks = np.concatenate([[0, 11, len(sites) - 1], rng.choice(len(sites), size=21, replace=False)])
+    cut, tol = lat.neighbor_cutoff_dist['Fe:Fe'][0], lat.neighbor_cutoff_dist_tol['Fe:Fe'][0]
+    cell = sc.cell_matrix
+    shifts = np.array([[a, b, c] for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)], dtype=float) @ cell
+    for e in picks:
+        d0 = sc.coordinates[sites] - sc.coordinates[sites[e]]                  # (n_centres, 3)
+        cand = d0[:, None, :] + shifts[None, :, :]                             # all 27 images, literally
+        r = np.sqrt((cand * cand).sum(axis=2))
+        best = r.argmin(axis=1)
+        rmin = r[np.arange(len(sites)), best]
+        vmin = cand[np.arange(len(sites)), best]
+        for hi in range(2):
+            sel = np.nonzero((rmin > cut[hi] - tol[hi]) & (rmin <= cut[hi] + tol[hi]))[0]
+            row = tabs[hi].index[e]
+            assert np.array_equal(row[row >= 0], sites[sel]), (e, hi)
+            assert np.abs(tabs[hi].vector[e][:len(sel)] - vmin[sel]).max() < 1e-9
+    tab = HopTables(lat, sc, sc.hop_neighbor_tables(), 'electron')
+    assert tab.nn == 4 and tab.n_centres == 12000
+
+
 def test_hop_list_roundtrip_in_reference_pickle_format(tmp_path):
     ex = H.load_example('hematite')
     t = ex.supercell.hop_neighbor_tables()
@@ -257,6 +290,42 @@ def test_hdf5_writer_layout(tmp_path):
         assert f['coordinates'].attrs['units'] == 'nanometers'
         assert f['time'].shape == (5,) and f['time'].attrs['units'] == 'picoseconds'
         assert list(f['topology/atoms/index'][:]) == [0, 1]
+
+
+def test_hdf5_layout_through_the_h5py_api(tmp_path, monkeypatch):
+    """The writer's LAYOUT (PyCD/hdf5_io.py:59-101, docs/hdf5_format.md:31-49) checked through an in-memory
+    recorder of the h5py API (tests/fake_h5py.py): h5py is absent from this image and from the GPU box, so the
+    real-file test above is skipped there; this one always runs.  Also: material_run's hdf5_output hook."""
+    import importlib
+    import fake_h5py
+    monkeypatch.setitem(sys.modules, 'h5py', fake_h5py)
+    import pycd_b200.hdf5_io as hio
+    hio = importlib.reload(hio)
+    try:
+        assert hio.HDF5_AVAILABLE
+        n_frames, n_car, dt_au = 7, 3, 413.4137
+        rng = np.random.default_rng(0)
+        uw = rng.normal(size=(n_frames, 3 * n_car)) * 40.0                      # bohr, (n_path, 3C) like unwrapped_traj.npy
+        assert hio.write_trajectory_h5(tmp_path / 'trajectory.h5', uw, n_car, dt_au)
+        f = fake_h5py.FILES[str(tmp_path / 'trajectory.h5')]
+        assert set(f.keys()) == {'coordinates', 'time', 'topology'} and set(f['topology'].keys()) == {'atoms'}
+        c, t = f['coordinates'], f['time']
+        assert c.shape == (n_frames, n_car, 3) and c.dtype == np.float32 and c.compression == 'gzip' and c.chunks
+        assert c.attrs['units'] == 'nanometers'
+        # bohr -> nm: coords / ANG2BOHR * 0.1 (PyCD/hdf5_io.py:120, 157); 1 bohr = 0.0529177 nm
+        assert np.allclose(c[:], (uw.reshape(n_frames, n_car, 3) * 0.052917721).astype(np.float32), rtol=1e-6)
+        assert t.shape == (n_frames,) and t.dtype == np.float64 and t.compression == 'gzip'
+        assert t.attrs['units'] == 'picoseconds'
+        # a.u. of time -> ps: AUTIME2PS = 2.4188843e-5 (PyCD/hdf5_io.py:124, 158); frames sit on the grid tau * dt
+        assert np.allclose(t[:], np.arange(n_frames) * dt_au * 2.418884326e-5, rtol=1e-8)
+        atoms = f['topology/atoms']
+        assert set(atoms.keys()) == {'name', 'element', 'index'}
+        assert atoms['name'].dtype == np.dtype('S10') and list(atoms['name'][:]) == [b'ATOM0', b'ATOM1', b'ATOM2']
+        assert atoms['element'].dtype == np.dtype('S2') and list(atoms['element'][:]) == [b'C'] * 3
+        assert atoms['index'].dtype == np.int32 and list(atoms['index'][:]) == [0, 1, 2]
+    finally:
+        monkeypatch.delitem(sys.modules, 'h5py')
+        importlib.reload(hio)
 
 
 def test_product_never_imports_the_oracle():
