@@ -111,6 +111,16 @@ typedef struct {
 int pycd_ewald_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int64_t row_begin,
                     int64_t row_end, double *out, pycd_ewald_stats *stats);
 
+/* The rows of unit cell 0, out[n_basis, N] = P[0:n_basis, :], for a fully periodic supercell whose sites are
+ * unit cell 0 plus lattice translations (site = cell * n_basis + basis, cell = (x*ny + y)*nz + z): the
+ * reciprocal-space sum of core.py:853-878 factorised by residue classes of the k indices modulo the supercell
+ * size -- one pass over the k vectors for the n_basis^2 basis pairs, then a Fourier transform over the
+ * n_cells classes (csrc/ewald_cells.cu): n_cells times fewer flops than pycd_ewald_rows(0, n_basis), same sum.
+ * Fails with "not translation-invariant ..." when the coordinates / matrices do not have that structure
+ * (callers then use pycd_ewald_rows). */
+int pycd_ewald_unit_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int32_t n_basis, const int32_t size[3],
+                         double *out, pycd_ewald_stats *stats);
+
 /* Translation-symmetric expansion (valid for pbc = [1,1,1]): given
  * Pu[n_basis, N] = P[0:n_basis, :] (the rows of unit cell 0) produce
  * out[(row_end-row_begin), N] with P[i,j] = Pu[b_i, (cell_j - cell_i mod size)*n_basis + b_j].

@@ -15,7 +15,7 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PKG_DIR / 'csrc'
 LIB_PATH = PKG_DIR / 'libpycd_b200.so'
-SOURCES = ['ctx.cu', 'ewald.cu', 'kmc.cu', 'kmc_stencil_nn4.cu', 'kmc_stencil_nn8.cu', 'kmc_stencil_nn12.cu',
+SOURCES = ['ctx.cu', 'ewald.cu', 'ewald_cells.cu', 'kmc.cu', 'kmc_stencil_nn4.cu', 'kmc_stencil_nn8.cu', 'kmc_stencil_nn12.cu',
            'msd.cu']
 HEADERS = ['common.cuh', 'kmc_types.cuh', 'kmc_stencil.cuh', 'kmc_stencil_launch.h']
 OBJ_DIR = CSRC_DIR / 'build'
@@ -137,6 +137,8 @@ _SIGNATURES = {
     'pycd_host_free': (C.c_int, [C.c_void_p]),
     'pycd_ewald_rows': (C.c_int, [C.c_void_p, C.POINTER(EwaldDesc), C.c_int64, C.c_int64,
                                   C.c_void_p, C.POINTER(EwaldStats)]),
+    'pycd_ewald_unit_rows': (C.c_int, [C.c_void_p, C.POINTER(EwaldDesc), C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                       C.POINTER(EwaldStats)]),
     'pycd_ewald_expand': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                                     C.c_int64, C.c_int64, C.c_void_p]),
     'pycd_kmc_system_create': (C.c_int, [C.c_void_p, C.POINTER(KmcSystemDesc),

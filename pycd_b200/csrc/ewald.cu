@@ -785,6 +785,25 @@ static void launch_fourier_pipe(pycd_ctx *ctx, const double *theta, long long n,
     check_launch(ctx, "ewald_fourier_pipe_kernel");
 }
 
+// real-space + self terms + final combination of rows [0, n_rows) whose reciprocal-space sums are in
+// `partials` (one partial): shared by the class-factorised unit-cell rows (ewald_cells.cu)
+void ewald_finish_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, const double *coords_dev, long long n,
+                       long long n_rows, const double *partials, double *out_dev) {
+    FinishParams fp;
+    for (int k = 0; k < 9; ++k) fp.cell[k] = desc->cell[k];
+    invert3(desc->cell, fp.cellinv);
+    for (int k = 0; k < 3; ++k) fp.pbc[k] = desc->pbc[k];
+    fp.sqrt_alpha = sqrt(desc->alpha);
+    fp.r_cut = desc->r_cut;
+    fp.eps = desc->dielectric;
+    fp.self_term = -sqrt(desc->alpha / M_PI) / desc->dielectric;  // core.py:1659
+    fp.fourier_only = 0;
+    const long long total = n_rows * n;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)ctx->n_sm * 16);
+    ewald_finish_kernel<<<blocks, 256, 0, ctx->stream>>>(coords_dev, n, 0, n_rows, fp, partials, 1, out_dev);
+    check_launch(ctx, "ewald_finish_kernel");
+}
+
 }  // namespace pycd
 
 using namespace pycd;

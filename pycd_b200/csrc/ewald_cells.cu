@@ -1,0 +1,301 @@
+// ewald_cells.cu -- reciprocal-space part of the UNIT-CELL ROWS of the Ewald array under full periodic
+// boundaries, factorised by residue classes of the k indices modulo the supercell size.
+//
+// The reference sums, for every site pair, cos(k.d_ij) over all half-space k vectors of the SUPERCELL
+// (PyCD/core.py:853-878): 4 N^2 K_eff flop in the structure-factor form of ewald.cu, 4 n_b N K_eff for the
+// rows of unit cell 0.  With sites r = tau_b + R (R = x a1 + y a2 + z a3, a_i = unit-cell vectors) and
+// k = n.B (B reciprocal to the supercell s_i a_i):   k.R = 2 pi sum_i n_i R_i / s_i,   which depends on n only
+// through the residues p_i = n_i mod s_i.  Hence, for a site b of cell 0 and a site b' of cell R,
+//
+//   F(b, b', R) = 2 sum_k w_k cos(k.(tau_b' - tau_b) + phi_p(R)),     phi_p(R) = 2 pi sum_i p_i R_i / s_i
+//               = 2 sum_p [ cos phi_p(R) C_p(b,b') - sin phi_p(R) S_p(b,b') ]
+//   C_p(b,b') = sum_{k in class p} w_k cos(k.(tau_b' - tau_b)),   S_p likewise with sin
+//
+// i.e. ONE pass over the k vectors for the n_b^2 basis pairs (class sums, kernel A: 4 n_b^2 K_eff flop --
+// n_cells times fewer than the rows of unit cell 0, 1000x at Hematite 10x10x10) followed by a discrete Fourier
+// transform over the n_cells classes per basis pair (kernel B).  Same sum, different order: agrees with the
+// DMMA kernels of ewald.cu to ~1e-15 max|P| (tests/test_gpu_configs.py).  The k vectors are enumerated on the
+// device, class by class (no host k list); real-space and self terms come from ewald_finish_kernel as before.
+#include "common.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace pycd {
+
+struct FinishParams;   // ewald.cu
+void ewald_finish_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, const double *coords_dev, long long n,
+                       long long n_rows, const double *partials, double *out_dev);   // ewald.cu
+
+struct CellParams {
+    int nb, sx, sy, sz;
+    int kmax[3];
+    double B[9];          // supercell reciprocal rows
+    double coeff;         // 2 pi / V
+    double alpha4, kc2;
+};
+
+constexpr int EC_THREADS = 256;
+constexpr int EC_KCH = 8;        // k vectors per accumulation sub-chunk
+
+// ---- kernel A: class sums.  grid = (n_classes, pair tiles); a thread owns basis b and 4 consecutive b'
+__global__ void __launch_bounds__(EC_THREADS)
+ewald_class_sums_kernel(CellParams P, const double *__restrict__ theta /* [nb][3] = B.tau_b */,
+                        double *__restrict__ Cs, double *__restrict__ Ss /* [class][nb][nb] */,
+                        unsigned long long *__restrict__ k_count)
+{
+    extern __shared__ double sm[];
+    const int nb = P.nb;
+    double *s_c = sm;                       // [KCH][nb]  cos(k.tau_b)
+    double *s_s = s_c + EC_KCH * nb;        // [KCH][nb]  sin
+    double *s_w = s_s + EC_KCH * nb;        // [EC_THREADS] weights of the valid k of a batch
+    int *s_n = reinterpret_cast<int *>(s_w + EC_THREADS);   // [EC_THREADS][3]
+    __shared__ int s_cnt, s_warp[EC_THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cls = blockIdx.x;
+    const int p3 = cls % P.sz, p2 = (cls / P.sz) % P.sy, p1 = cls / (P.sz * P.sy);
+    // my pairs: b fixed, b' = 4 g .. 4 g + 3
+    const int groups = (nb + 3) / 4;
+    const int item = blockIdx.y * EC_THREADS + tid;
+    const bool has_item = item < nb * groups;
+    const int b = has_item ? item / groups : 0, g4 = has_item ? (item - b * groups) * 4 : 0;
+    double accC[4] = {0, 0, 0, 0}, accS[4] = {0, 0, 0, 0};
+
+    // candidates of the class: n_i = p_i + s_i m_i inside [-kmax_i, kmax_i] (n3 >= 0: half space
+    // n3 > 0 | (n3 == 0, n2 > 0) | (n3 == n2 == 0, n1 > 0), the one ewald.cu's k list uses)
+    auto lo_m = [](int p, int s, int kmax) { return -((kmax + p) / s); };                // smallest m with n >= -kmax
+    auto hi_m = [](int p, int s, int kmax) { return (kmax - p) >= 0 ? (kmax - p) / s : -1; };
+    const int m1lo = lo_m(p1, P.sx, P.kmax[0]), m1hi = hi_m(p1, P.sx, P.kmax[0]);
+    const int m2lo = lo_m(p2, P.sy, P.kmax[1]), m2hi = hi_m(p2, P.sy, P.kmax[1]);
+    const int m3lo = 0, m3hi = hi_m(p3, P.sz, P.kmax[2]);
+    const long long M1 = m1hi - m1lo + 1, M2 = m2hi - m2lo + 1, M3 = m3hi - m3lo + 1;
+    const long long n_cand = (M1 > 0 && M2 > 0 && M3 > 0) ? M1 * M2 * M3 : 0;
+    unsigned long long my_valid = 0;
+
+    for (long long base = 0; base < n_cand; base += EC_THREADS) {
+        // ---- test one candidate per thread, compact the valid ones into s_n / s_w
+        const long long c = base + tid;
+        bool ok = false;
+        int n1 = 0, n2 = 0, n3 = 0;
+        double w = 0.0;
+        if (c < n_cand) {
+            const int i3 = (int)(c % M3), i2 = (int)((c / M3) % M2), i1 = (int)(c / (M3 * M2));
+            n1 = p1 + P.sx * (m1lo + i1);
+            n2 = p2 + P.sy * (m2lo + i2);
+            n3 = p3 + P.sz * (m3lo + i3);
+            const bool half = n3 > 0 || (n3 == 0 && (n2 > 0 || (n2 == 0 && n1 > 0)));
+            const double kx = n1 * P.B[0] + n2 * P.B[3] + n3 * P.B[6];
+            const double ky = n1 * P.B[1] + n2 * P.B[4] + n3 * P.B[7];
+            const double kz = n1 * P.B[2] + n2 * P.B[5] + n3 * P.B[8];
+            const double k2 = kx * kx + ky * ky + kz * kz;
+            ok = half && (k2 < P.kc2);
+            if (ok) w = P.coeff * exp(-k2 / P.alpha4) / k2;   // core.py:869-875
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+        for (int q = 0; q < EC_THREADS / 32; ++q) {
+            if (q < wid) off += s_warp[q];
+            total += s_warp[q];
+        }
+        if (ok) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            s_n[3 * pos] = n1; s_n[3 * pos + 1] = n2; s_n[3 * pos + 2] = n3;
+            s_w[pos] = w;
+        }
+        if (tid == 0) s_cnt = total;
+        my_valid += ok ? 1ull : 0ull;
+        __syncthreads();
+        const int n_valid = s_cnt;
+        // ---- accumulate the valid k of the batch, EC_KCH at a time
+        for (int k0 = 0; k0 < n_valid; k0 += EC_KCH) {
+            const int kn = min(EC_KCH, n_valid - k0);
+            for (int e = tid; e < kn * nb; e += EC_THREADS) {
+                const int kk = e / nb, bb = e - kk * nb;
+                const int *nn = s_n + 3 * (k0 + kk);
+                const double arg = fma((double)nn[0], theta[3 * bb], fma((double)nn[1], theta[3 * bb + 1],
+                                                                          (double)nn[2] * theta[3 * bb + 2]));
+                double sv, cv;
+                sincos(arg, &sv, &cv);
+                s_c[kk * nb + bb] = cv;
+                s_s[kk * nb + bb] = sv;
+            }
+            __syncthreads();
+            if (has_item) {
+                for (int kk = 0; kk < kn; ++kk) {
+                    const double wk = s_w[k0 + kk];
+                    const double wc = wk * s_c[kk * nb + b], ws = wk * s_s[kk * nb + b];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int bp = min(g4 + i, nb - 1);
+                        const double cp = s_c[kk * nb + bp], sp = s_s[kk * nb + bp];
+                        accC[i] = fma(wc, cp, fma(ws, sp, accC[i]));       // w cos(k.(tau_b' - tau_b))
+                        accS[i] = fma(wc, sp, fma(-ws, cp, accS[i]));      // w sin(k.(tau_b' - tau_b))
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (has_item) {
+        const long long o = ((long long)cls * nb + b) * nb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (g4 + i < nb) {
+                Cs[o + g4 + i] = accC[i];
+                Ss[o + g4 + i] = accS[i];
+            }
+    }
+    if (blockIdx.y == 0 && my_valid) atomicAdd(k_count, my_valid);
+}
+
+// ---- kernel B: transform over the classes.  f[b][(R, b')] = sum_p cos(phi_p(R)) C_p - sin(phi_p(R)) S_p.
+// One thread per output element; phase factors from per-axis tables e^{2 pi i t / s_i} in shared memory.
+__global__ void __launch_bounds__(256)
+ewald_class_dft_kernel(CellParams P, const double *__restrict__ Cs, const double *__restrict__ Ss,
+                       long long n_sites, double *__restrict__ f)
+{
+    extern __shared__ double tab[];   // cos / sin tables of the three axes
+    const int nb = P.nb;
+    double *cx = tab, *sxp = cx + P.sx, *cy = sxp + P.sx, *syp = cy + P.sy, *cz = syp + P.sy, *szp = cz + P.sz;
+    for (int t = threadIdx.x; t < P.sx; t += blockDim.x) sincospi(2.0 * t / P.sx, &sxp[t], &cx[t]);
+    for (int t = threadIdx.x; t < P.sy; t += blockDim.x) sincospi(2.0 * t / P.sy, &syp[t], &cy[t]);
+    for (int t = threadIdx.x; t < P.sz; t += blockDim.x) sincospi(2.0 * t / P.sz, &szp[t], &cz[t]);
+    __syncthreads();
+    const long long total = (long long)nb * n_sites;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int b = (int)(idx / n_sites);
+    const int j = (int)(idx - (long long)b * n_sites);
+    const int cell = j / nb, bp = j - cell * nb;
+    const int R3 = cell % P.sz, R2 = (cell / P.sz) % P.sy, R1 = cell / (P.sz * P.sy);
+    const long long pair = (long long)b * nb + bp, stride = (long long)nb * nb;
+    double acc = 0.0;
+    int t1 = 0;
+    for (int p1 = 0; p1 < P.sx; ++p1) {
+        const double c1 = cx[t1], s1 = sxp[t1];
+        int t2 = 0;
+        for (int p2 = 0; p2 < P.sy; ++p2) {
+            const double c12 = c1 * cy[t2] - s1 * syp[t2], s12 = s1 * cy[t2] + c1 * syp[t2];
+            int t3 = 0;
+            const long long cls0 = ((long long)p1 * P.sy + p2) * P.sz;
+            for (int p3 = 0; p3 < P.sz; ++p3) {
+                const double cph = c12 * cz[t3] - s12 * szp[t3], sph = s12 * cz[t3] + c12 * szp[t3];
+                const long long o = (cls0 + p3) * stride + pair;
+                acc = fma(cph, Cs[o], fma(-sph, Ss[o], acc));
+                t3 += R3; t3 -= t3 >= P.sz ? P.sz : 0;
+            }
+            t2 += R2; t2 -= t2 >= P.sy ? P.sy : 0;
+        }
+        t1 += R1; t1 -= t1 >= P.sx ? P.sx : 0;
+    }
+    f[idx] = acc;
+}
+
+}  // namespace pycd
+
+using namespace pycd;
+
+extern "C" int pycd_ewald_unit_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, int32_t n_basis,
+                                    const int32_t size[3], double *out, pycd_ewald_stats *stats) {
+    return guarded([&] {
+        NvtxRange nvtx("pycd.ewald_unit_rows");
+        PYCD_REQUIRE(ctx && desc && size && out, "NULL argument");
+        const int nb = n_basis, sx = size[0], sy = size[1], sz = size[2];
+        PYCD_REQUIRE(nb > 0 && nb <= 255 && sx > 0 && sy > 0 && sz > 0, "bad supercell");
+        const long long cells = (long long)sx * sy * sz, n = cells * nb;
+        PYCD_REQUIRE(n == desc->n_sites, "n_basis * cells != n_sites");
+        PYCD_REQUIRE(desc->pbc[0] && desc->pbc[1] && desc->pbc[2], "the class factorisation needs pbc = [1, 1, 1]");
+        PYCD_REQUIRE(desc->alpha > 0 && desc->volume > 0 && desc->dielectric > 0, "bad Ewald parameters");
+        DeviceGuard g(ctx);
+        cudaStream_t s = ctx->stream;
+        // ---- what the factorisation assumes, verified on the host: sites = tau_b + x a1 + y a2 + z a3 with
+        // a_i = (row i of the simulation cell) / s_i, and B reciprocal to that cell (the reference
+        // builds the two matrices differently; they agree for the shapes it supports)
+        std::vector<double> xyz((size_t)n * 3);
+        PYCD_CUDA(cudaMemcpy(xyz.data(), desc->coords, sizeof(double) * n * 3, cudaMemcpyDefault));
+        double a[3][3];
+        const int ss[3] = {sx, sy, sz};
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) a[i][c] = desc->cell[3 * i + c] / ss[i];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const double dot = desc->recip[3 * j] * a[i][0] + desc->recip[3 * j + 1] * a[i][1] + desc->recip[3 * j + 2] * a[i][2];
+                const double want = (i == j) ? 2 * M_PI / ss[i] : 0.0;
+                if (fabs(dot - want) > 1e-9)
+                    throw Error("not translation-invariant: the reciprocal matrix is not the dual of the simulation cell");
+            }
+        double scale = 0.0;
+        for (int c = 0; c < 9; ++c) scale = std::max(scale, fabs(desc->cell[c]));
+        for (long long cell = 0; cell < cells; ++cell) {
+            const int z = (int)(cell % sz), y = (int)((cell / sz) % sy), x = (int)(cell / ((long long)sz * sy));
+            for (int b = 0; b < nb; ++b)
+                for (int c = 0; c < 3; ++c) {
+                    const double want = xyz[3 * b + c] + x * a[0][c] + y * a[1][c] + z * a[2][c];
+                    if (fabs(xyz[3 * (cell * nb + b) + c] - want) > 1e-9 * scale)
+                        throw Error("not translation-invariant: site coordinates are not unit cell 0 plus lattice translations");
+                }
+        }
+        CellParams P;
+        P.nb = nb; P.sx = sx; P.sy = sy; P.sz = sz;
+        for (int c = 0; c < 3; ++c) P.kmax[c] = desc->k_max[c];
+        for (int c = 0; c < 9; ++c) P.B[c] = desc->recip[c];
+        P.coeff = (2 * M_PI) / desc->volume;
+        P.alpha4 = 4 * desc->alpha;
+        P.kc2 = desc->k_cut * desc->k_cut;
+        std::vector<double> theta_h((size_t)nb * 3);
+        for (int b = 0; b < nb; ++b)
+            for (int j = 0; j < 3; ++j)
+                theta_h[3 * b + j] = desc->recip[3 * j] * xyz[3 * b] + desc->recip[3 * j + 1] * xyz[3 * b + 1] +
+                                     desc->recip[3 * j + 2] * xyz[3 * b + 2];
+        DevBuf<double> theta, Cs, Ss, f, coords_dev;
+        DevBuf<unsigned long long> kcount;
+        theta.alloc(theta_h.size());
+        PYCD_CUDA(cudaMemcpyAsync(theta.p, theta_h.data(), sizeof(double) * theta_h.size(), cudaMemcpyHostToDevice, s));
+        coords_dev.alloc((size_t)n * 3);
+        PYCD_CUDA(cudaMemcpyAsync(coords_dev.p, xyz.data(), sizeof(double) * n * 3, cudaMemcpyHostToDevice, s));
+        const size_t cs_n = (size_t)cells * nb * nb;
+        Cs.alloc(cs_n);
+        Ss.alloc(cs_n);
+        f.alloc((size_t)nb * n);
+        kcount.alloc(1);
+        kcount.zero(s);
+        OutBuf<double> o;
+        o.bind(out, (size_t)nb * n);
+
+        KernelTimer tf(ctx, KC_EWALD_FOURIER);
+        {
+            const int groups = (nb + 3) / 4;
+            const unsigned tiles = (unsigned)((nb * groups + EC_THREADS - 1) / EC_THREADS);
+            const size_t smem = sizeof(double) * (2 * (size_t)EC_KCH * nb + EC_THREADS) + sizeof(int) * 3 * EC_THREADS;
+            PYCD_REQUIRE(cells < (1ll << 31) && tiles < 65536, "grid too large");
+            ewald_class_sums_kernel<<<dim3((unsigned)cells, tiles), EC_THREADS, smem, s>>>(P, theta.p, Cs.p, Ss.p, kcount.p);
+            check_launch(ctx, "ewald_class_sums_kernel");
+            const long long total = (long long)nb * n;
+            const size_t tsm = sizeof(double) * 2 * (size_t)(sx + sy + sz);
+            ewald_class_dft_kernel<<<(unsigned)((total + 255) / 256), 256, tsm, s>>>(P, Cs.p, Ss.p, n, f.p);
+            check_launch(ctx, "ewald_class_dft_kernel");
+        }
+        tf.stop(2);
+        KernelTimer tr(ctx, KC_EWALD_FINISH);
+        ewald_finish_rows(ctx, desc, coords_dev.p, n, nb, f.p, o.dev());
+        tr.stop(1);
+        unsigned long long k_eff = 0;
+        PYCD_CUDA(cudaMemcpyAsync(&k_eff, kcount.p, sizeof(k_eff), cudaMemcpyDeviceToHost, s));
+        o.finish(s);
+        PYCD_CUDA(cudaStreamSynchronize(s));
+        tf.read();
+        tr.read();
+        if (stats) {
+            stats->k_eff = (int64_t)k_eff;
+            stats->rows = nb;
+            stats->fourier_ms = ctx->last_ms[KC_EWALD_FOURIER];
+            stats->finish_ms = ctx->last_ms[KC_EWALD_FINISH];
+            stats->flops = 8.0 * (double)nb * nb * (double)k_eff + 4.0 * (double)nb * (double)n * (double)cells +
+                           40.0 * (double)nb * (double)n;
+            stats->k_split = 1;
+        }
+    });
+}

@@ -92,6 +92,38 @@ def ewald_rows(ctx, params, coords, row_begin, row_end, out=None, plan_rows=0, k
                  'finish_ms': stats.finish_ms, 'flops': stats.flops, 'k_split': stats.k_split}
 
 
+def unit_cell_rows(ctx, params, coords=None, out=None, method='auto'):
+    """P[0:n_per_cell, :] of a fully periodic supercell -- what the step kernel reads (unit-rows layout) and what
+    the translation expansion starts from.  method 'cells' = the class-factorised sum (pycd_ewald_unit_rows:
+    one pass over the k vectors for the n_per_cell^2 basis pairs + a Fourier transform over the cells),
+    'rows' = pycd_ewald_rows(0, n_per_cell) (the DMMA kernel: 4 n_per_cell N K_eff flop), 'auto' = cells when
+    the geometry has the structure it needs, else rows."""
+    sc = params.supercell
+    n = sc.num_system_elements
+    if coords is None:
+        coords = np.ascontiguousarray(sc.coordinates)
+    if method not in ('auto', 'cells', 'rows'):
+        raise ValueError(f"method must be auto, cells or rows, not {method!r}")
+    if method != 'rows':
+        if out is None:
+            out = np.empty((sc.n_per_cell, n))
+        desc = params.desc(coords)
+        stats = nat.EwaldStats()
+        size = (C.c_int32 * 3)(*[int(v) for v in sc.system_size])
+        rc = nat.lib().pycd_ewald_unit_rows(ctx.handle, C.byref(desc), int(sc.n_per_cell), size, nat.ptr(out),
+                                            C.byref(stats))
+        if rc == 0:
+            return out, {'k_eff': stats.k_eff, 'rows': stats.rows, 'fourier_ms': stats.fourier_ms,
+                         'finish_ms': stats.finish_ms, 'flops': stats.flops, 'k_split': stats.k_split,
+                         'method': 'cells'}
+        msg = nat.lib().pycd_last_error().decode(errors='replace')
+        if method == 'cells' or 'not translation-invariant' not in msg and 'pbc' not in msg:
+            raise nat.NativeError(msg)
+    out, st = ewald_rows(ctx, params, coords, 0, sc.n_per_cell, out=out)
+    st['method'] = 'rows'
+    return out, st
+
+
 def ewald_expand(ctx, supercell, p_unit, row_begin, row_end, out=None):
     """Rows of the full array from the unit-cell-0 rows (pycd_ewald_expand)."""
     n = supercell.num_system_elements
@@ -127,7 +159,7 @@ def precomputed_array(ctx, params, coords=None, symmetric=None, row_begin=0, row
         out, stats = ewald_rows(ctx, params, coords, row_begin, row_end, out)
         stats['symmetric'] = False
         return out, stats
-    p_unit, stats = ewald_rows(ctx, params, coords, 0, sc.n_per_cell)
+    p_unit, stats = unit_cell_rows(ctx, params, coords)
     out = ewald_expand(ctx, sc, p_unit, row_begin, row_end, out)
     stats['symmetric'] = True
     stats['expand_ms'] = ctx.last_kernel_ms(nat.KC_EWALD_EXPAND)

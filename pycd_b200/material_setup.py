@@ -63,8 +63,7 @@ def material_setup(input_directory_path, system_size, pbc, generate_hop_neighbor
         want_dense = (not symmetric) or n * n * 8 <= limit
         P = None
         if symmetric:
-            p_unit, _ = ew.ewald_rows(ctx, ep, np.ascontiguousarray(supercell.coordinates), 0,
-                                      supercell.n_per_cell)
+            p_unit, _ = ew.unit_cell_rows(ctx, ep, np.ascontiguousarray(supercell.coordinates))
             np.save(input_directory_path / UNIT_ROWS_FILE, p_unit)
             if want_dense:
                 P = ew.ewald_expand(ctx, supercell, p_unit, 0, n)

@@ -18,13 +18,10 @@ OUT = ROOT / 'scratch' / 'ab'
 
 VARIANTS = {
     'default': [],
-    'dummy_store_off': ['-DPYCD_DUMMY_STORE=0'],
-    'owner_late': ['-DPYCD_OWNER_EARLY=0'],
-    'patch_early': ['-DPYCD_PATCH_EARLY=1'],
-    'one_chain': ['-DPYCD_SUM_CHAINS=1'],
-    'exp_library': ['-DPYCD_EXP_TABLE=0'],
-    'owner_loads_last': ['-DPYCD_OWNER_LOADS_FIRST=0'],
-    'h1_select': ['-DPYCD_H1_PRED=0'],
+    'total_first_off': ['-DPYCD_TOTAL_FIRST=0'],
+    'vote_branch_off': ['-DPYCD_VOTE_BRANCH=0'],
+    'red_ptx_off': ['-DPYCD_RED_PTX=0'],
+    'all_three_off': ['-DPYCD_TOTAL_FIRST=0', '-DPYCD_VOTE_BRANCH=0', '-DPYCD_RED_PTX=0'],
 }
 # a header from the history compiled against today's kmc_types.cuh: HEADER@<git rev>
 HISTORY = {'committed_dc5ad1f': 'dc5ad1f'}
