@@ -365,12 +365,16 @@ def main():
     # N x N array by lattice translation.  Every rank does both itself: at 2 ms per 7.2 GB the local expansion
     # is cheaper than an NVLink all-gather of row blocks (measured 22 ms at 8 GPUs), so the symmetric path needs
     # NO collective; the row-sharded dense evaluation + all-gather is the cfg-4 leg (`configs.cfg4_ewald`).
-    t0 = time.perf_counter()
-    _, est = EW.unit_cell_rows(ctx, ep, coords.data_ptr(), out=p_unit.data_ptr())
-    EW.ewald_expand(ctx, sc, p_unit.data_ptr(), 0, N, out=P.data_ptr())
-    expand_ms = ctx.last_kernel_ms(nat.KC_EWALD_EXPAND)
-    torch.cuda.synchronize()
-    ewald_seconds = time.perf_counter() - t0
+    def precompute():
+        t0 = time.perf_counter()
+        _, st = EW.unit_cell_rows(ctx, ep, coords.data_ptr(), out=p_unit.data_ptr())
+        EW.ewald_expand(ctx, sc, p_unit.data_ptr(), 0, N, out=P.data_ptr())
+        ms = ctx.last_kernel_ms(nat.KC_EWALD_EXPAND)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, st, ms
+    # first call at this size (pays the allocator's first large blocks), then the reported one
+    ewald_first, _, _ = precompute()
+    ewald_seconds, est, expand_ms = precompute()
     # for the record (untimed above): the same rows through the DMMA kernel, k list split over the ranks + one
     # all-reduce -- the FP64 roofline kernel of the general path (partial periodic boundaries, dense rows)
     p_chk = torch.empty_like(p_unit)
@@ -389,8 +393,8 @@ def main():
     rows_seconds = time.perf_counter() - t1
     diff = float((p_chk - p_unit).abs().max() / p_unit.abs().max())
     del p_chk
-    ewald_info = {'seconds': round(ewald_seconds, 4), 'k_eff': est['k_eff'], 'rows_direct': sc.n_per_cell,
-                  'method': est.get('method'), 'fourier_ms': round(est['fourier_ms'], 3),
+    ewald_info = {'seconds': round(ewald_seconds, 4), 'seconds_first_call': round(ewald_first, 4), 'k_eff': est['k_eff'],
+                  'rows_direct': sc.n_per_cell, 'method': est.get('method'), 'fourier_ms': round(est['fourier_ms'], 3),
                   'finish_ms': round(est['finish_ms'], 3), 'expand_ms': round(expand_ms, 3),
                   'collectives': 'none (every rank evaluates the unit-cell rows and expands the array itself)',
                   'dmma_rows_path': {'seconds': round(rows_seconds, 4), 'fourier_ms': round(est_rows['fourier_ms'], 3),

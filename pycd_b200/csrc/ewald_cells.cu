@@ -19,6 +19,8 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace pycd {
@@ -194,6 +196,82 @@ ewald_class_dft_kernel(CellParams P, const double *__restrict__ Cs, const double
     f[idx] = acc;
 }
 
+// ---- kernel B, separable form: the transform over the classes axis by axis through shared memory.  A CTA owns
+// basis site b and PB consecutive b' (contiguous output runs): Z_p = C_p + i S_p of its pairs for ALL classes is
+// loaded once (n_cells * PB complex numbers), then three passes (z, y, x) of s_axis complex multiply-adds per
+// element -- n_cells (sx + sy + sz) instead of n_cells^2 operations per pair, and C_p, S_p are read exactly once.
+template <int PB>
+__global__ void __launch_bounds__(256)
+ewald_class_dft3_kernel(CellParams P, const double *__restrict__ Cs, const double *__restrict__ Ss,
+                        long long n_sites, double *__restrict__ f)
+{
+    extern __shared__ __align__(16) double sm3[];
+    const int nb = P.nb, sx = P.sx, sy = P.sy, sz = P.sz;
+    const int cells = sx * sy * sz;
+    double2 *za = reinterpret_cast<double2 *>(sm3);            // [cells][PB]
+    double2 *zb = za + (size_t)cells * PB;                     // [cells][PB]
+    double *cx = reinterpret_cast<double *>(zb + (size_t)cells * PB);
+    double *sxp = cx + sx, *cy = sxp + sx, *syp = cy + sy, *cz = syp + sy, *szp = cz + sz;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < sx; t += blockDim.x) sincospi(2.0 * t / sx, &sxp[t], &cx[t]);
+    for (int t = tid; t < sy; t += blockDim.x) sincospi(2.0 * t / sy, &syp[t], &cy[t]);
+    for (int t = tid; t < sz; t += blockDim.x) sincospi(2.0 * t / sz, &szp[t], &cz[t]);
+    const int b = blockIdx.x, bp0 = blockIdx.y * PB;
+    const int total = cells * PB;
+    for (int o = tid; o < total; o += blockDim.x) {
+        const int q = o % PB, cls = o / PB;
+        const int bp = min(bp0 + q, nb - 1);
+        const long long src = ((long long)cls * nb + b) * nb + bp;
+        za[o] = make_double2(Cs[src], Ss[src]);
+    }
+    __syncthreads();
+    // pass z: zb[(p1,p2,R3)] = sum_p3 e^{2 pi i p3 R3 / sz} za[(p1,p2,p3)]
+    for (int o = tid; o < total; o += blockDim.x) {
+        const int q = o % PB, u = o / PB;
+        const int R3 = u % sz, p12 = u / sz;
+        double re = 0.0, im = 0.0;
+        int t = 0;
+        for (int p3 = 0; p3 < sz; ++p3) {
+            const double2 z = za[(p12 * sz + p3) * PB + q];
+            const double c = cz[t], sn = szp[t];
+            re = fma(c, z.x, fma(-sn, z.y, re));
+            im = fma(c, z.y, fma(sn, z.x, im));
+            t += R3; t -= t >= sz ? sz : 0;
+        }
+        zb[o] = make_double2(re, im);
+    }
+    __syncthreads();
+    // pass y: za[(p1,R2,R3)] = sum_p2 e^{2 pi i p2 R2 / sy} zb[(p1,p2,R3)]
+    for (int o = tid; o < total; o += blockDim.x) {
+        const int q = o % PB, u = o / PB;
+        const int R3 = u % sz, R2 = (u / sz) % sy, p1 = u / (sz * sy);
+        double re = 0.0, im = 0.0;
+        int t = 0;
+        for (int p2 = 0; p2 < sy; ++p2) {
+            const double2 z = zb[((p1 * sy + p2) * sz + R3) * PB + q];
+            const double c = cy[t], sn = syp[t];
+            re = fma(c, z.x, fma(-sn, z.y, re));
+            im = fma(c, z.y, fma(sn, z.x, im));
+            t += R2; t -= t >= sy ? sy : 0;
+        }
+        za[o] = make_double2(re, im);
+    }
+    __syncthreads();
+    // pass x (real part only): f[b][(R, b')] = Re sum_p1 e^{2 pi i p1 R1 / sx} za[(p1,R2,R3)]
+    for (int o = tid; o < total; o += blockDim.x) {
+        const int q = o % PB, u = o / PB;
+        const int R23 = u % (sz * sy), R1 = u / (sz * sy);
+        double re = 0.0;
+        int t = 0;
+        for (int p1 = 0; p1 < sx; ++p1) {
+            const double2 z = za[(p1 * sy * sz + R23) * PB + q];
+            re = fma(cx[t], z.x, fma(-sxp[t], z.y, re));
+            t += R1; t -= t >= sx ? sx : 0;
+        }
+        if (bp0 + q < nb) f[(long long)b * n_sites + (long long)u * nb + bp0 + q] = re;
+    }
+}
+
 }  // namespace pycd
 
 using namespace pycd;
@@ -273,9 +351,25 @@ extern "C" int pycd_ewald_unit_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, 
             PYCD_REQUIRE(cells < (1ll << 31) && tiles < 65536, "grid too large");
             ewald_class_sums_kernel<<<dim3((unsigned)cells, tiles), EC_THREADS, smem, s>>>(P, theta.p, Cs.p, Ss.p, kcount.p);
             check_launch(ctx, "ewald_class_sums_kernel");
-            const long long total = (long long)nb * n;
+            // separable transform when the classes of 4 / 2 / 1 pairs fit in shared memory twice, else the direct one
             const size_t tsm = sizeof(double) * 2 * (size_t)(sx + sy + sz);
-            ewald_class_dft_kernel<<<(unsigned)((total + 255) / 256), 256, tsm, s>>>(P, Cs.p, Ss.p, n, f.p);
+            auto need = [&](int pb) { return 2 * sizeof(double2) * (size_t)cells * pb + tsm; };
+            const size_t cap = 200 * 1024;
+            const char *force = getenv("PYCD_EWALD_DFT");   // "direct": A/B against the one-thread-per-element form
+            const bool direct = force && std::string(force) == "direct";
+            if (!direct && need(4) <= cap) {
+                PYCD_CUDA(cudaFuncSetAttribute(ewald_class_dft3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(4)));
+                ewald_class_dft3_kernel<4><<<dim3(nb, (nb + 3) / 4), 256, need(4), s>>>(P, Cs.p, Ss.p, n, f.p);
+            } else if (!direct && need(2) <= cap) {
+                PYCD_CUDA(cudaFuncSetAttribute(ewald_class_dft3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(2)));
+                ewald_class_dft3_kernel<2><<<dim3(nb, (nb + 1) / 2), 256, need(2), s>>>(P, Cs.p, Ss.p, n, f.p);
+            } else if (!direct && need(1) <= cap) {
+                PYCD_CUDA(cudaFuncSetAttribute(ewald_class_dft3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(1)));
+                ewald_class_dft3_kernel<1><<<dim3(nb, nb), 256, need(1), s>>>(P, Cs.p, Ss.p, n, f.p);
+            } else {
+                const long long total = (long long)nb * n;
+                ewald_class_dft_kernel<<<(unsigned)((total + 255) / 256), 256, tsm, s>>>(P, Cs.p, Ss.p, n, f.p);
+            }
             check_launch(ctx, "ewald_class_dft_kernel");
         }
         tf.stop(2);
