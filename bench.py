@@ -360,23 +360,9 @@ def main():
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    # ---- the timed precompute: rows of unit cell 0 by the class-factorised sum (csrc/ewald_cells.cu: one pass
-    # over the k vectors for the n_per_cell^2 basis pairs + a Fourier transform over the cells), then the dense
-    # N x N array by lattice translation.  Every rank does both itself: at 2 ms per 7.2 GB the local expansion
-    # is cheaper than an NVLink all-gather of row blocks (measured 22 ms at 8 GPUs), so the symmetric path needs
-    # NO collective; the row-sharded dense evaluation + all-gather is the cfg-4 leg (`configs.cfg4_ewald`).
-    def precompute():
-        t0 = time.perf_counter()
-        _, st = EW.unit_cell_rows(ctx, ep, coords.data_ptr(), out=p_unit.data_ptr())
-        EW.ewald_expand(ctx, sc, p_unit.data_ptr(), 0, N, out=P.data_ptr())
-        ms = ctx.last_kernel_ms(nat.KC_EWALD_EXPAND)
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0, st, ms
-    # first call at this size (pays the allocator's first large blocks), then the reported one
-    ewald_first, _, _ = precompute()
-    ewald_seconds, est, expand_ms = precompute()
-    # for the record (untimed above): the same rows through the DMMA kernel, k list split over the ranks + one
-    # all-reduce -- the FP64 roofline kernel of the general path (partial periodic boundaries, dense rows)
+    # ---- first, for the record and to bring the idle GPU up to its clocks (the host spent seconds building tables):
+    # the same rows through the DMMA kernel, k list split over the ranks + one all-reduce -- the FP64 roofline
+    # kernel of the general path (partial periodic boundaries, dense rows)
     p_chk = torch.empty_like(p_unit)
     torch.cuda.synchronize()
     if dist:
@@ -391,6 +377,25 @@ def main():
         torch.cuda.synchronize()
         t_reduce = time.perf_counter() - tr
     rows_seconds = time.perf_counter() - t1
+    # ---- the timed precompute: rows of unit cell 0 by the class-factorised sum (csrc/ewald_cells.cu: one pass
+    # over the k vectors for the n_per_cell^2 basis pairs + a Fourier transform over the cells), then the dense
+    # N x N array by lattice translation.  Every rank does both itself: at 2 ms per 7.2 GB the local expansion
+    # is cheaper than an NVLink all-gather of row blocks (measured 22 ms at 8 GPUs), so the symmetric path needs
+    # NO collective; the row-sharded dense evaluation + all-gather is the cfg-4 leg (`configs.cfg4_ewald`).
+    def precompute():
+        t0 = time.perf_counter()
+        _, st = EW.unit_cell_rows(ctx, ep, coords.data_ptr(), out=p_unit.data_ptr())
+        ta = time.perf_counter()
+        EW.ewald_expand(ctx, sc, p_unit.data_ptr(), 0, N, out=P.data_ptr())
+        ms = ctx.last_kernel_ms(nat.KC_EWALD_EXPAND)
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
+        if os.environ.get('PYCD_BENCH_DEBUG'):
+            print(f'precompute: unit rows {1e3 * (ta - t0):.2f} ms, expansion {1e3 * (tb - ta):.2f} ms', file=sys.stderr)
+        return tb - t0, st, ms
+    # first call at this size (pays the allocator's first large blocks), then the reported one
+    ewald_first, _, _ = precompute()
+    ewald_seconds, est, expand_ms = precompute()
     diff = float((p_chk - p_unit).abs().max() / p_unit.abs().max())
     del p_chk
     ewald_info = {'seconds': round(ewald_seconds, 4), 'seconds_first_call': round(ewald_first, 4), 'k_eff': est['k_eff'],

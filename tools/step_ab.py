@@ -18,10 +18,11 @@ OUT = ROOT / 'scratch' / 'ab'
 
 VARIANTS = {
     'default': [],
-    'total_first_off': ['-DPYCD_TOTAL_FIRST=0'],
-    'vote_branch_off': ['-DPYCD_VOTE_BRANCH=0'],
-    'red_ptx_off': ['-DPYCD_RED_PTX=0'],
-    'all_three_off': ['-DPYCD_TOTAL_FIRST=0', '-DPYCD_VOTE_BRANCH=0', '-DPYCD_RED_PTX=0'],
+    'shuffle_scan_and_sums': ['-DPYCD_SCAN_DMMA=0', '-DPYCD_SUM_DMMA=0'],
+    'helper_warp_off': ['-DPYCD_HELPER_WARP=0'],
+    'flat_tail_off': ['-DPYCD_FLAT_TAIL=0'],
+    'owner_late': ['-DPYCD_OWNER_EARLY=0'],
+    'exp_library': ['-DPYCD_EXP_TABLE=0'],
 }
 # a header from the history compiled against today's kmc_types.cuh: HEADER@<git rev>
 HISTORY = {'committed_dc5ad1f': 'dc5ad1f'}
