@@ -2,13 +2,13 @@
 """SASS of the production step kernel's hot loop, with the mnemonics DESIGN.md 4.3 talks about counted.
 
 usage: sass_excerpt.py <libpycd_b200.so> <out.txt>
-Takes kmc_step_warp_kernel<2,1,4,INCR=true,PLAIN=true> (the benchmark shape) out of `cuobjdump -sass`, finds
+Takes kmc_step_warp_kernel<2,1,4,INCR=true,MODE=0 (plain)> (the benchmark shape) out of `cuobjdump -sass`, finds
 the burst loop (the last backward branch of the function that spans the DMMAs) and writes that range."""
 import re
 import subprocess
 import sys
 
-FUN = '_ZN4pycd20kmc_step_warp_kernelILi2ELi1ELi4ELb1ELb1EEEvNS_6SysDevENS_10StencilDevENS_6EnsDevENS_11AdvanceArgsE'
+FUN = '_ZN4pycd20kmc_step_warp_kernelILi2ELi1ELi4ELb1ELi0EEEvNS_6SysDevENS_10StencilDevENS_6EnsDevENS_11AdvanceArgsE'
 
 
 def main():
