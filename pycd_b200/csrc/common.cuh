@@ -51,6 +51,8 @@ struct pycd_ctx {
     void *flush_buf = nullptr;
     int flush_value = 0;
     cudaStream_t copy_stream = nullptr;   // pipelined read-back (pycd_kmc_read_begin / _end)
+    void *arena = nullptr;                // work buffers of the synchronous entry points (grow-only, see Arena)
+    size_t arena_bytes = 0;
 };
 
 namespace pycd {
@@ -93,6 +95,33 @@ struct DevBuf {
     }
     void zero(cudaStream_t s) {
         if (p) PYCD_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+};
+
+// Work buffers of one synchronous entry point, carved out of the context's grow-only arena: no cudaMalloc /
+// cudaFree pair per call (each costs 0.1-0.5 ms, more than the kernels of a small job).  One user at a time:
+// the entry points that take it synchronise the stream before they return.
+struct Arena {
+    pycd_ctx *ctx;
+    size_t need = 0, used = 0;
+    explicit Arena(pycd_ctx *c) : ctx(c) {}
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    void reserve(size_t bytes) { need += pad(bytes); }
+    void commit() {
+        if (need > ctx->arena_bytes) {
+            if (ctx->arena) cudaFree(ctx->arena);
+            ctx->arena = nullptr;
+            ctx->arena_bytes = 0;
+            PYCD_CUDA(cudaMalloc(&ctx->arena, need));
+            ctx->arena_bytes = need;
+        }
+    }
+    template <typename T>
+    T *take(size_t count) {
+        T *p = reinterpret_cast<T *>(static_cast<char *>(ctx->arena) + used);
+        used += pad(count * sizeof(T));
+        if (used > ctx->arena_bytes) throw Error("arena overrun");
+        return p;
     }
 };
 

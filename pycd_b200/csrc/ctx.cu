@@ -71,6 +71,7 @@ int pycd_ctx_destroy(pycd_ctx *ctx) {
             for (int j = 0; j < 2; ++j)
                 if (ctx->ev[k][j]) cudaEventDestroy(ctx->ev[k][j]);
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+        if (ctx->arena) cudaFree(ctx->arena);
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
         cudaStreamDestroy(ctx->stream);

@@ -13,6 +13,8 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdint>
+#include <type_traits>
 #include <cstdlib>
 #include <algorithm>
 
@@ -661,31 +663,40 @@ ewald_finish_kernel(const double *__restrict__ coords, long long n_sites, long l
 // (row i, x index of the target cell); for every y the sz*nb elements of the z column are contiguous in the
 // output AND in the source row up to one wrap (source offset = target offset - z_i*nb, + sz*nb if negative),
 // so an element costs a compare, two adds, a load from the L2-resident unit-cell rows and a coalesced store --
-// no division per element (the first version spent its time in five 64-bit divisions per element).
+// no division per element (the first version spent its time in five 64-bit divisions per element).  The
+// sy*sz*nb elements of one (row, x) are walked as ONE flat range (a z column of 300 elements would leave
+// 212 of 512 thread slots idle when walked by itself); V = 2: 16-byte loads and stores when nb is even
+// (every run, wrap point and row start is then an even offset).
+template <int V>
 __global__ void __launch_bounds__(256)
 ewald_expand_kernel(const double *__restrict__ pu, int nb, int sx, int sy, int sz,
                     long long n_sites, long long row0, long long n_rows, double *__restrict__ out)
 {
+    using Vec = typename std::conditional<V == 2, double2, double>::type;
     const int xj = blockIdx.x;
+    const int szn = sz * nb;
+    const int szv = szn / V;                      // vector elements per z column
+    const int per_x = sy * szv;
+    const int q256 = 256 / szv, r256 = 256 - q256 * szv;
     for (long long il = blockIdx.y; il < n_rows; il += gridDim.y) {
         const int i = (int)(row0 + il);
         const int ci = i / nb, bi = i - ci * nb;
         const int zi = ci % sz, yi = (ci / sz) % sy, xi = ci / (sz * sy);
         int ddx = xj - xi;
         ddx += ddx < 0 ? sx : 0;
-        const int szn = sz * nb, shift = zi * nb;
-        const double *src_row = pu + (long long)bi * n_sites;
-        double *dst_row = out + il * n_sites + (long long)xj * sy * szn;
-        for (int yj = threadIdx.y; yj < sy; yj += blockDim.y) {
+        const int shiftv = zi * nb / V;
+        const Vec *src_x = reinterpret_cast<const Vec *>(pu + (long long)bi * n_sites + (long long)ddx * sy * szn);
+        Vec *dst = reinterpret_cast<Vec *>(out + il * n_sites + (long long)xj * sy * szn);
+        int yj = threadIdx.x / szv, e = threadIdx.x - yj * szv;
+        for (int f = threadIdx.x; f < per_x; f += 256) {
             int ddy = yj - yi;
             ddy += ddy < 0 ? sy : 0;
-            const double *src = src_row + (long long)(ddx * sy + ddy) * szn;
-            double *dst = dst_row + (long long)yj * szn;
-            for (int e = threadIdx.x; e < szn; e += blockDim.x) {
-                int se = e - shift;
-                se += se < 0 ? szn : 0;
-                dst[e] = __ldg(src + se);
-            }
+            int se = e - shiftv;
+            se += se < 0 ? szv : 0;
+            dst[f] = __ldg(src_x + ddy * szv + se);
+            e += r256;
+            yj += q256;
+            if (e >= szv) { e -= szv; ++yj; }
         }
     }
 }
@@ -971,13 +982,14 @@ extern "C" int pycd_ewald_expand(pycd_ctx *ctx, const double *p_unit, int32_t n_
         OutBuf<double> o;
         o.bind(out, (size_t)n_rows * n);
         KernelTimer t(ctx, KC_EWALD_EXPAND);
-        // threads: x over the z column of a target cell row (sz*nb contiguous elements), y over the y index
-        const int szn = size[2] * n_basis;
-        const unsigned tx = szn >= 256 ? 256u : (szn > 128 ? 128u : (szn > 64 ? 64u : 32u));
-        const dim3 block(tx, 256u / tx);
         const dim3 grid((unsigned)size[0], (unsigned)std::min<long long>(n_rows, 65535));
-        ewald_expand_kernel<<<grid, block, 0, ctx->stream>>>(pu.p, n_basis, size[0], size[1], size[2], n,
-                                                             row_begin, n_rows, o.dev());
+        const bool vec2 = n_basis % 2 == 0 && ((uintptr_t)pu.p % 16) == 0 && ((uintptr_t)o.dev() % 16) == 0;
+        if (vec2)
+            ewald_expand_kernel<2><<<grid, 256, 0, ctx->stream>>>(pu.p, n_basis, size[0], size[1], size[2], n,
+                                                                  row_begin, n_rows, o.dev());
+        else
+            ewald_expand_kernel<1><<<grid, 256, 0, ctx->stream>>>(pu.p, n_basis, size[0], size[1], size[2], n,
+                                                                  row_begin, n_rows, o.dev());
         check_launch(ctx, "ewald_expand_kernel");
         t.stop(1);
         o.finish(ctx->stream);

@@ -18,6 +18,7 @@
 // device, class by class (no host k list); real-space and self terms come from ewald_finish_kernel as before.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <string>
@@ -40,29 +41,40 @@ struct CellParams {
 constexpr int EC_THREADS = 256;
 constexpr int EC_KCH = 8;        // k vectors per accumulation sub-chunk
 
-// ---- kernel A: class sums.  grid = (n_classes, pair tiles); a thread owns basis b and 4 consecutive b'
-__global__ void __launch_bounds__(EC_THREADS)
+// ---- kernel A: class sums.  grid = (n_classes, pair tiles).  A thread owns a 2 x 4 tile of basis pairs
+// (b, b+1) x (b'..b'+3): per k vector 7 shared-memory loads (weight, 2 x 16 bytes of cos/sin of its b pair,
+// 4 x 16 bytes of its four b') feed 32 FMAs -- the first version (1 x 4 tile, 11 eight-byte loads per 16 FMAs)
+// ran at 86 % of the shared-memory wavefront peak with the FP64 pipe 29 % busy.  When the pairs need fewer
+// than 256 threads, `ks` groups of `ipad` threads take the k vectors of a sub-chunk in turn and their partial
+// sums are added in group order at the end (fixed order: results do not depend on scheduling).
+__global__ void __launch_bounds__(EC_THREADS, 2)
 ewald_class_sums_kernel(CellParams P, const double *__restrict__ theta /* [nb][3] = B.tau_b */,
                         double *__restrict__ Cs, double *__restrict__ Ss /* [class][nb][nb] */,
-                        unsigned long long *__restrict__ k_count)
+                        unsigned long long *__restrict__ k_count, int ipad, int ks)
 {
-    extern __shared__ double sm[];
-    const int nb = P.nb;
-    double *s_c = sm;                       // [KCH][nb]  cos(k.tau_b)
-    double *s_s = s_c + EC_KCH * nb;        // [KCH][nb]  sin
-    double *s_w = s_s + EC_KCH * nb;        // [EC_THREADS] weights of the valid k of a batch
+    extern __shared__ __align__(16) double sm[];
+    const int nb = P.nb, nbp = (nb + 3) & ~3;
+    double *s_c = sm;                       // [KCH][nbp]  cos(k.tau_b), rows padded with zeros
+    double *s_s = s_c + EC_KCH * nbp;       // [KCH][nbp]  sin
+    double *s_w = s_s + EC_KCH * nbp;       // [EC_THREADS] weights of the valid k of a batch
     int *s_n = reinterpret_cast<int *>(s_w + EC_THREADS);   // [EC_THREADS][3]
     __shared__ int s_cnt, s_warp[EC_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int cls = blockIdx.x;
     const int p3 = cls % P.sz, p2 = (cls / P.sz) % P.sy, p1 = cls / (P.sz * P.sy);
-    // my pairs: b fixed, b' = 4 g .. 4 g + 3
-    const int groups = (nb + 3) / 4;
-    const int item = blockIdx.y * EC_THREADS + tid;
-    const bool has_item = item < nb * groups;
-    const int b = has_item ? item / groups : 0, g4 = has_item ? (item - b * groups) * 4 : 0;
-    double accC[4] = {0, 0, 0, 0}, accS[4] = {0, 0, 0, 0};
+    // my pairs: b = 2 q, 2 q + 1; b' = 4 g .. 4 g + 3; my k vectors: slot, slot + ks, ... of every sub-chunk
+    const int groups = nbp / 4, n_items = ((nb + 1) / 2) * groups;
+    const int slot = tid / ipad, local = tid - slot * ipad;
+    const int item = blockIdx.y * ipad + local;
+    const bool has_item = slot < ks && item < n_items;
+    const int b0 = has_item ? 2 * (item / groups) : 0, g4 = has_item ? (item % groups) * 4 : 0;
+    double accC[2][4], accS[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) accC[j][i] = accS[j][i] = 0.0;
+    for (int e = tid; e < 2 * EC_KCH * nbp; e += EC_THREADS) sm[e] = 0.0;
 
     // candidates of the class: n_i = p_i + s_i m_i inside [-kmax_i, kmax_i] (n3 >= 0: half space
     // n3 > 0 | (n3 == 0, n2 > 0) | (n3 == n2 == 0, n1 > 0), the one ewald.cu's k list uses)
@@ -121,34 +133,70 @@ ewald_class_sums_kernel(CellParams P, const double *__restrict__ theta /* [nb][3
                                                                           (double)nn[2] * theta[3 * bb + 2]));
                 double sv, cv;
                 sincos(arg, &sv, &cv);
-                s_c[kk * nb + bb] = cv;
-                s_s[kk * nb + bb] = sv;
+                s_c[kk * nbp + bb] = cv;
+                s_s[kk * nbp + bb] = sv;
             }
             __syncthreads();
             if (has_item) {
-                for (int kk = 0; kk < kn; ++kk) {
+                for (int kk = slot; kk < kn; kk += ks) {
                     const double wk = s_w[k0 + kk];
-                    const double wc = wk * s_c[kk * nb + b], ws = wk * s_s[kk * nb + b];
+                    const double *rc = s_c + kk * nbp, *rs = s_s + kk * nbp;
+                    const double2 cb = *reinterpret_cast<const double2 *>(rc + b0);
+                    const double2 sb = *reinterpret_cast<const double2 *>(rs + b0);
+                    const double2 c01 = *reinterpret_cast<const double2 *>(rc + g4);
+                    const double2 c23 = *reinterpret_cast<const double2 *>(rc + g4 + 2);
+                    const double2 s01 = *reinterpret_cast<const double2 *>(rs + g4);
+                    const double2 s23 = *reinterpret_cast<const double2 *>(rs + g4 + 2);
+                    const double wc[2] = {wk * cb.x, wk * cb.y}, ws[2] = {wk * sb.x, wk * sb.y};
+                    const double cp[4] = {c01.x, c01.y, c23.x, c23.y}, sp[4] = {s01.x, s01.y, s23.x, s23.y};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int bp = min(g4 + i, nb - 1);
-                        const double cp = s_c[kk * nb + bp], sp = s_s[kk * nb + bp];
-                        accC[i] = fma(wc, cp, fma(ws, sp, accC[i]));       // w cos(k.(tau_b' - tau_b))
-                        accS[i] = fma(wc, sp, fma(-ws, cp, accS[i]));      // w sin(k.(tau_b' - tau_b))
-                    }
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            accC[j][i] = fma(wc[j], cp[i], fma(ws[j], sp[i], accC[j][i]));    // w cos(k.(tau_b' - tau_b))
+                            accS[j][i] = fma(wc[j], sp[i], fma(-ws[j], cp[i], accS[j][i]));   // w sin(k.(tau_b' - tau_b))
+                        }
                 }
             }
             __syncthreads();
         }
     }
-    if (has_item) {
-        const long long o = ((long long)cls * nb + b) * nb;
+    // ---- partial sums of the k slots, added in slot order (the scratch aliases the panels: all reads are done)
+    if (ks > 1) {
+        __syncthreads();
+        double *red = sm;                   // [slot][16][ipad]
+        if (has_item && slot > 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (g4 + i < nb) {
-                Cs[o + g4 + i] = accC[i];
-                Ss[o + g4 + i] = accS[i];
-            }
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    red[((slot * 16) + j * 4 + i) * ipad + local] = accC[j][i];
+                    red[((slot * 16) + 8 + j * 4 + i) * ipad + local] = accS[j][i];
+                }
+        }
+        __syncthreads();
+        if (has_item && slot == 0)
+            for (int q = 1; q < ks; ++q)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        accC[j][i] += red[((q * 16) + j * 4 + i) * ipad + local];
+                        accS[j][i] += red[((q * 16) + 8 + j * 4 + i) * ipad + local];
+                    }
+    }
+    if (has_item && slot == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (b0 + j >= nb) continue;
+            const long long o = ((long long)cls * nb + b0 + j) * nb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (g4 + i < nb) {
+                    Cs[o + g4 + i] = accC[j][i];
+                    Ss[o + g4 + i] = accS[j][i];
+                }
+        }
     }
     if (blockIdx.y == 0 && my_valid) atomicAdd(k_count, my_valid);
 }
@@ -328,28 +376,43 @@ extern "C" int pycd_ewald_unit_rows(pycd_ctx *ctx, const pycd_ewald_desc *desc, 
             for (int j = 0; j < 3; ++j)
                 theta_h[3 * b + j] = desc->recip[3 * j] * xyz[3 * b] + desc->recip[3 * j + 1] * xyz[3 * b + 1] +
                                      desc->recip[3 * j + 2] * xyz[3 * b + 2];
-        DevBuf<double> theta, Cs, Ss, f, coords_dev;
-        DevBuf<unsigned long long> kcount;
-        theta.alloc(theta_h.size());
-        PYCD_CUDA(cudaMemcpyAsync(theta.p, theta_h.data(), sizeof(double) * theta_h.size(), cudaMemcpyHostToDevice, s));
-        coords_dev.alloc((size_t)n * 3);
-        PYCD_CUDA(cudaMemcpyAsync(coords_dev.p, xyz.data(), sizeof(double) * n * 3, cudaMemcpyHostToDevice, s));
+        // work buffers from the context's arena (six cudaMalloc / cudaFree pairs cost more than the kernels)
+        struct { double *p; } theta, Cs, Ss, f, coords_dev;
+        struct { unsigned long long *p; } kcount;
         const size_t cs_n = (size_t)cells * nb * nb;
-        Cs.alloc(cs_n);
-        Ss.alloc(cs_n);
-        f.alloc((size_t)nb * n);
-        kcount.alloc(1);
-        kcount.zero(s);
+        Arena arena(ctx);
+        arena.reserve(sizeof(double) * theta_h.size());
+        arena.reserve(sizeof(double) * (size_t)n * 3);
+        arena.reserve(sizeof(double) * cs_n);
+        arena.reserve(sizeof(double) * cs_n);
+        arena.reserve(sizeof(double) * (size_t)nb * n);
+        arena.reserve(sizeof(unsigned long long));
+        arena.commit();
+        theta.p = arena.take<double>(theta_h.size());
+        coords_dev.p = arena.take<double>((size_t)n * 3);
+        Cs.p = arena.take<double>(cs_n);
+        Ss.p = arena.take<double>(cs_n);
+        f.p = arena.take<double>((size_t)nb * n);
+        kcount.p = arena.take<unsigned long long>(1);
+        PYCD_CUDA(cudaMemcpyAsync(theta.p, theta_h.data(), sizeof(double) * theta_h.size(), cudaMemcpyHostToDevice, s));
+        if (is_device_pointer(desc->coords)) coords_dev.p = const_cast<double *>(desc->coords);
+        else PYCD_CUDA(cudaMemcpyAsync(coords_dev.p, xyz.data(), sizeof(double) * n * 3, cudaMemcpyHostToDevice, s));
+        PYCD_CUDA(cudaMemsetAsync(kcount.p, 0, sizeof(unsigned long long), s));
         OutBuf<double> o;
         o.bind(out, (size_t)nb * n);
 
         KernelTimer tf(ctx, KC_EWALD_FOURIER);
         {
-            const int groups = (nb + 3) / 4;
-            const unsigned tiles = (unsigned)((nb * groups + EC_THREADS - 1) / EC_THREADS);
-            const size_t smem = sizeof(double) * (2 * (size_t)EC_KCH * nb + EC_THREADS) + sizeof(int) * 3 * EC_THREADS;
+            const int nbp = (nb + 3) & ~3;
+            const int n_items = ((nb + 1) / 2) * (nbp / 4);
+            const int ipad = std::min(EC_THREADS, (n_items + 31) & ~31);
+            const int ks = std::min(EC_KCH, EC_THREADS / ipad);
+            const unsigned tiles = (unsigned)((n_items + ipad - 1) / ipad);
+            const size_t panels = sizeof(double) * (2 * (size_t)EC_KCH * nbp + EC_THREADS) + sizeof(int) * 3 * EC_THREADS;
+            const size_t smem = std::max(panels, ks > 1 ? sizeof(double) * 16 * (size_t)ks * ipad : (size_t)0);
             PYCD_REQUIRE(cells < (1ll << 31) && tiles < 65536, "grid too large");
-            ewald_class_sums_kernel<<<dim3((unsigned)cells, tiles), EC_THREADS, smem, s>>>(P, theta.p, Cs.p, Ss.p, kcount.p);
+            ewald_class_sums_kernel<<<dim3((unsigned)cells, tiles), EC_THREADS, smem, s>>>(P, theta.p, Cs.p, Ss.p, kcount.p,
+                                                                                           ipad, ks);
             check_launch(ctx, "ewald_class_sums_kernel");
             // separable transform when the classes of 4 / 2 / 1 pairs fit in shared memory twice, else the direct one
             const size_t tsm = sizeof(double) * 2 * (size_t)(sx + sy + sz);

@@ -132,6 +132,30 @@ def test_class_factorised_unit_rows_full_size_cfg3_and_cfg4(ctx, cfg4):
     assert st_p['method'] == 'rows'
 
 
+@pytest.mark.parametrize('nb,size', [(5, (3, 2, 4)), (30, (3, 4, 10)), (24, (2, 3, 13)), (7, (2, 2, 41)), (2, (1, 1, 3))])
+def test_translation_expansion_equals_the_index_map(ctx, nb, size):
+    """pycd_ewald_expand against P[i, j] = Pu[b_i, ((cell_j - cell_i) mod size) * nb + b_j] written with numpy:
+    odd basis counts (8-byte path) and even ones (16-byte path), z columns shorter and longer than a CTA,
+    row ranges that start and end inside a cell."""
+    from types import SimpleNamespace
+    sx, sy, sz = size
+    n = nb * sx * sy * sz
+    rng = np.random.default_rng(nb * 1000 + sz)
+    pu = rng.standard_normal((nb, n))
+    sc = SimpleNamespace(num_system_elements=n, system_size=size, n_per_cell=nb)
+    site = np.arange(n)
+    cell, b = site // nb, site % nb
+    cx, cy, cz = cell // (sy * sz), (cell // sz) % sy, cell % sz
+    for r0, r1 in ((0, n), (1, min(n, nb + 3)), (n - 2, n)):
+        rows = np.arange(r0, r1)
+        dx = (cx[None, :] - cx[rows, None]) % sx
+        dy = (cy[None, :] - cy[rows, None]) % sy
+        dz = (cz[None, :] - cz[rows, None]) % sz
+        want = pu[b[rows, None], ((dx * sy + dy) * sz + dz) * nb + b[None, :]]
+        got = EW.ewald_expand(ctx, sc, pu, r0, r1)
+        assert np.array_equal(got, want)
+
+
 def test_unit_cell_rows_summed_from_k_range_parts(ctx):
     """The unit-cell rows sharded by k range (bench.py / N GPUs: every rank sums one part of the k list,
     one all-reduce adds the parts): the sum of the parts equals the one-call rows to rounding, for part
