@@ -440,16 +440,21 @@ def main():
         for _ in range(warmup):
             if not args.no_flush:
                 ctx.flush_l2()        # also allocates the 512 MB flush buffer outside the timed region
-            ens.advance_resident(S)
+            ens.advance_async(S)
+        ens.wait()
         barrier()
         ctx.reset_timers()
         l0 = ctx.launch_count()
         sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
         t0 = time.perf_counter()
+        # the launches are enqueued back to back (pycd_kmc_advance_async: no host round trip per launch, so
+        # host jitter -- other ranks, the NVML sampler -- cannot open gaps between them); wait() + barrier
+        # close the timed region
         for _ in range(steps):
             if not args.no_flush:
-                ctx.flush_l2()            # 512 MB memset between timed iterations
-            ens.advance_resident(S)
+                ctx.flush_l2()            # 512 MB memset between timed iterations (stream-ordered)
+            ens.advance_async(S)
+        ens.wait()
         barrier()
         wall = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None

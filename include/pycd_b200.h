@@ -53,7 +53,7 @@ double pycd_ctx_last_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
 double pycd_ctx_total_kernel_ms(pycd_ctx *ctx, int32_t kernel_class);
 int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t kernel_class);
 int pycd_ctx_reset_timers(pycd_ctx *ctx);
-/* evict the L2 (512 MB memset on the context's stream); for cold-cache timing */
+/* evict the L2 (512 MB memset enqueued on the context's stream, no host synchronisation); for cold-cache timing */
 int pycd_ctx_flush_l2(pycd_ctx *ctx);
 
 /* Page-locked host buffers for the end-to-end path (host numpy views over them make the
@@ -221,6 +221,16 @@ int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *occupancy0, u
 int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
                      int32_t *events_out, double *times_out, int64_t *steps_done,
                      int64_t *n_active);
+
+/* Batch production without a host round trip per launch (counter-based RNG modes, no per-step outputs):
+ * pycd_kmc_advance_async only enqueues the step kernel on the context's stream; any number of calls may be
+ * in flight, interleaved with pycd_ctx_flush_l2 / pycd_kmc_read_begin / pycd_kmc_ensemble_reset (all
+ * stream-ordered).  pycd_kmc_wait blocks until they have finished, reports the unfinished trajectories and
+ * accounts the kernel times (pycd_ctx_total_kernel_ms).  The kernel shape is chosen from the number of
+ * unfinished trajectories known at the last synchronising call.  The reference loop has no counterpart:
+ * its trajectories run one after the other on the host (core.py:2787-2861). */
+int pycd_kmc_advance_async(pycd_kmc_ensemble *ens, int64_t max_steps);
+int pycd_kmc_wait(pycd_kmc_ensemble *ens, int64_t *n_active);
 
 /* State read-back; any pointer may be NULL.  unwrapped: (n_traj, n_path, 3C) displacement
  * from the start site on the time grid (unwrapped_traj.npy, core.py:2852-2854);

@@ -149,6 +149,8 @@ _SIGNATURES = {
                                            C.POINTER(C.c_void_p)]),
     'pycd_kmc_ensemble_destroy': (C.c_int, [C.c_void_p]),
     'pycd_kmc_ensemble_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    'pycd_kmc_advance_async': (C.c_int, [C.c_void_p, C.c_int64]),
+    'pycd_kmc_wait': (C.c_int, [C.c_void_p, C.c_void_p]),
     'pycd_kmc_advance': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.POINTER(C.c_int64)]),
     'pycd_kmc_read': (C.c_int, [C.c_void_p] + [C.c_void_p] * 8),

@@ -53,6 +53,11 @@ struct pycd_ctx {
     cudaStream_t copy_stream = nullptr;   // pipelined read-back (pycd_kmc_read_begin / _end)
     void *arena = nullptr;                // work buffers of the synchronous entry points (grow-only, see Arena)
     size_t arena_bytes = 0;
+    // kernel timers of launches that were issued without a host synchronisation (pycd_kmc_advance_async):
+    // their event pairs wait here until collect_timers() adds them to the totals
+    struct Pending { cudaEvent_t a, b; int cls, n_launch; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace pycd {
@@ -162,26 +167,58 @@ struct OutBuf {
     }
 };
 
+inline cudaEvent_t pooled_event(pycd_ctx *ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->ev_pool.empty()) {
+        e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+    } else {
+        PYCD_CUDA(cudaEventCreate(&e));
+    }
+    return e;
+}
+
+// adds the deferred timers to the totals (blocks until their launches have finished)
+inline void collect_timers(pycd_ctx *ctx) {
+    for (const pycd_ctx::Pending &p : ctx->pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(p.b);
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        ctx->last_ms[p.cls] = ms;
+        ctx->total_ms[p.cls] += ms;
+        ctx->class_launches[p.cls] += p.n_launch;
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
 struct KernelTimer {
     pycd_ctx *ctx;
     int cls;
     int n_launch;
-    KernelTimer(pycd_ctx *c, int k) : ctx(c), cls(k), n_launch(0) {
-        cudaEventRecord(ctx->ev[cls][0], ctx->stream);
+    cudaEvent_t a, b;
+    // deferred = true: own event pair from the context's pool, so that several launches can be in flight
+    KernelTimer(pycd_ctx *c, int k, bool deferred = false) : ctx(c), cls(k), n_launch(0) {
+        a = deferred ? pooled_event(c) : c->ev[k][0];
+        b = deferred ? pooled_event(c) : c->ev[k][1];
+        cudaEventRecord(a, ctx->stream);
     }
     // stop() right after the launches (asynchronous); read() blocks on the stop event
     void stop(int launches_timed = 1) {
         n_launch = launches_timed;
-        cudaEventRecord(ctx->ev[cls][1], ctx->stream);
+        cudaEventRecord(b, ctx->stream);
     }
     void read() {
         float ms = 0.f;
-        cudaEventSynchronize(ctx->ev[cls][1]);
-        cudaEventElapsedTime(&ms, ctx->ev[cls][0], ctx->ev[cls][1]);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
         ctx->last_ms[cls] = ms;
         ctx->total_ms[cls] += ms;
         ctx->class_launches[cls] += n_launch;
     }
+    // instead of read(): leave the pair with the context (collect_timers)
+    void defer() { ctx->pending.push_back({a, b, cls, n_launch}); }
 };
 
 // NVTX range around a library call (visible to nsys / ncu --nvtx; a no-op without a tool attached)

@@ -70,6 +70,8 @@ int pycd_ctx_destroy(pycd_ctx *ctx) {
         for (int k = 0; k < KC_COUNT; ++k)
             for (int j = 0; j < 2; ++j)
                 if (ctx->ev[k][j]) cudaEventDestroy(ctx->ev[k][j]);
+        collect_timers(ctx);
+        for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
         if (ctx->arena) cudaFree(ctx->arena);
         cudaStreamSynchronize(ctx->copy_stream);
@@ -93,15 +95,26 @@ int pycd_ctx_info(pycd_ctx *ctx, int32_t *n_sm, int64_t *free_bytes, int64_t *to
 
 int64_t pycd_ctx_launch_count(pycd_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+// launches issued by pycd_kmc_advance_async are accounted when their events are collected
+static void settle(pycd_ctx *ctx) {
+    if (ctx && !ctx->pending.empty()) {
+        DeviceGuard g(ctx);
+        collect_timers(ctx);
+    }
+}
+
 double pycd_ctx_last_kernel_ms(pycd_ctx *ctx, int32_t k) {
+    settle(ctx);
     return (ctx && k >= 0 && k < KC_COUNT) ? ctx->last_ms[k] : -1.0;
 }
 
 double pycd_ctx_total_kernel_ms(pycd_ctx *ctx, int32_t k) {
+    settle(ctx);
     return (ctx && k >= 0 && k < KC_COUNT) ? ctx->total_ms[k] : -1.0;
 }
 
 int64_t pycd_ctx_class_launches(pycd_ctx *ctx, int32_t k) {
+    settle(ctx);
     return (ctx && k >= 0 && k < KC_COUNT) ? ctx->class_launches[k] : -1;
 }
 
@@ -112,8 +125,7 @@ int pycd_ctx_flush_l2(pycd_ctx *ctx) {
         const size_t bytes = (size_t)512 << 20;  // 4x the 126 MB L2
         if (!ctx->flush_buf) PYCD_CUDA(cudaMalloc(&ctx->flush_buf, bytes));
         ctx->flush_value ^= 0xff;
-        PYCD_CUDA(cudaMemsetAsync(ctx->flush_buf, ctx->flush_value, bytes, ctx->stream));
-        PYCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        PYCD_CUDA(cudaMemsetAsync(ctx->flush_buf, ctx->flush_value, bytes, ctx->stream));   // stream-ordered
     });
 }
 
@@ -142,6 +154,7 @@ int pycd_nvtx_pop(void) {
 
 int pycd_ctx_reset_timers(pycd_ctx *ctx) {
     if (!ctx) return 1;
+    settle(ctx);
     for (int k = 0; k < KC_COUNT; ++k) {
         ctx->total_ms[k] = 0;
         ctx->class_launches[k] = 0;

@@ -1758,9 +1758,11 @@ static void launch_step(pycd_ctx *ctx, bool compact, const SysDev &S, const EnsD
     else launch_step_impl<BS, false, 0, 0>(ctx, S, E, A, smem);
 }
 
-extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
-                                int32_t *events_out, double *times_out, int64_t *steps_done,
-                                int64_t *n_active) {
+// body of pycd_kmc_advance / pycd_kmc_advance_async.  in_flight = true: no host buffers, no host
+// synchronisation; the kernel timer is left with the context and the finished flags are read by pycd_kmc_wait
+static int advance_impl(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
+                        int32_t *events_out, double *times_out, int64_t *steps_done,
+                        int64_t *n_active, bool in_flight) {
     return guarded([&] {
         PYCD_REQUIRE(ens, "NULL ensemble");
         PYCD_REQUIRE(max_steps > 0, "max_steps must be positive");
@@ -1773,6 +1775,7 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         PYCD_REQUIRE(E.refresh_interval <= 1 || max_steps % E.refresh_interval == 0,
                      "max_steps must be a multiple of refresh_interval");
         PYCD_REQUIRE(E.rng_mode != PYCD_RNG_REPLAY || draws, "REPLAY mode needs draws");
+        PYCD_REQUIRE(!in_flight || E.rng_mode != PYCD_RNG_REPLAY, "pycd_kmc_advance_async needs a counter-based RNG mode");
         const size_t nt = (size_t)E.n_traj;
         cudaStream_t s = ctx->stream;
         InBuf<double> dr;
@@ -1794,7 +1797,7 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
         const size_t smem = kmc_smem_bytes(E.n_proc, E.C, ens->sys->dev.nn);
         PYCD_REQUIRE(smem <= 200 * 1024, "trajectory state does not fit in shared memory");
         const bool cp = ens->sys->compact;
-        KernelTimer tk(ctx, KC_KMC_STEP);
+        KernelTimer tk(ctx, KC_KMC_STEP, in_flight);
         // PYCD_KMC_VARIANT=process keeps the one-thread-per-process kernel for A/B measurements
         const char *kv = getenv("PYCD_KMC_VARIANT");
         const bool per_process = kv && std::string(kv) == "process";
@@ -1859,6 +1862,10 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
             launch_step_impl<256, true, 64, 4>(ctx, ens->sys->dev, E, A, smem);
         else launch_step<256>(ctx, cp, ens->sys->dev, E, A, smem);
         tk.stop(1);
+        if (in_flight) {
+            tk.defer();
+            return;
+        }
         ev.finish(s);
         tm.finish(s);
         sdn.finish(s);
@@ -1872,6 +1879,33 @@ extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const
             ens->n_active = act;
             if (n_active) *n_active = act;
         }
+    });
+}
+
+extern "C" int pycd_kmc_advance(pycd_kmc_ensemble *ens, int64_t max_steps, const double *draws,
+                                int32_t *events_out, double *times_out, int64_t *steps_done,
+                                int64_t *n_active) {
+    return advance_impl(ens, max_steps, draws, events_out, times_out, steps_done, n_active, false);
+}
+
+extern "C" int pycd_kmc_advance_async(pycd_kmc_ensemble *ens, int64_t max_steps) {
+    return advance_impl(ens, max_steps, nullptr, nullptr, nullptr, nullptr, nullptr, true);
+}
+
+extern "C" int pycd_kmc_wait(pycd_kmc_ensemble *ens, int64_t *n_active) {
+    return guarded([&] {
+        PYCD_REQUIRE(ens, "NULL ensemble");
+        pycd_ctx *ctx = ens->sys->ctx;
+        DeviceGuard g(ctx);
+        const size_t nt = (size_t)ens->dev.n_traj;
+        std::vector<int> done_h(nt);
+        PYCD_CUDA(cudaMemcpyAsync(done_h.data(), ens->done.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, ctx->stream));
+        PYCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        collect_timers(ctx);
+        int64_t act = 0;
+        for (int v : done_h) act += (v == 0);
+        ens->n_active = act;
+        if (n_active) *n_active = act;
     });
 }
 

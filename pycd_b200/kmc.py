@@ -353,6 +353,16 @@ class KmcEnsemble:
                                              C.byref(n_active)))
         return n_active.value
 
+    def advance_async(self, max_steps):
+        """Enqueue `max_steps` KMC steps without waiting (Philox mode, no per-step outputs); see wait()."""
+        nat.check(nat.lib().pycd_kmc_advance_async(self.handle, int(max_steps)))
+
+    def wait(self):
+        """Block until the launches of advance_async have finished; number of unfinished trajectories."""
+        n_active = C.c_int64()
+        nat.check(nat.lib().pycd_kmc_wait(self.handle, C.byref(n_active)))
+        return n_active.value
+
     def read(self, unwrapped=True, rates=False, out=None):
         """State read-back.  `out` may carry pre-allocated (e.g. pinned) arrays from a previous
         call (the returned dict) to avoid re-allocating the result buffers."""

@@ -389,6 +389,56 @@ def test_64_carriers_philox_matches_oracle(ctx, hematite_64e, layout, refresh):
     assert np.allclose(gg[3], one['dg0_grid'], rtol=1e-9, atol=1e-15)
 
 
+def test_batch_production_api_equals_the_synchronous_calls(ctx, hematite_64e):
+    """pycd_kmc_advance_async + pycd_kmc_wait (launches in flight, L2 flushes between them) and the
+    double-buffered read-back (pycd_kmc_read_begin / _end with re-armed batches in between) against plain
+    advance + read, and against the oracle: same sites, step counts, displacement grids; the kernel
+    timers account every launch that was in flight."""
+    run, p_unit, dense = hematite_64e
+    n_traj, burst, n_burst = 12, 256, 3
+    occ = K.philox_initial_occupancy(run.tables, n_traj, 64, seed=21)
+    kw = dict(dt_grid=run.time_interval / 3000, n_path=64, step_limit=burst * n_burst, stop_at_grid_end=False)
+    system = K.KmcSystem(ctx, run, p_unit, layout='unit_rows')
+    ens = K.KmcEnsemble(system, occ, rng_mode=nat.RNG_PHILOX, seed=21, refresh_interval=16, **kw)
+    for _ in range(n_burst):
+        ens.advance_resident(burst)
+    plain = ens.read()
+    # the same three launches without a host round trip, timers settled by wait()
+    ens.reset(occ, 0)
+    ctx.reset_timers()
+    l0 = ctx.launch_count()
+    for _ in range(n_burst):
+        ctx.flush_l2()
+        ens.advance_async(burst)
+    assert ens.wait() == 0          # step_limit reached: every trajectory finished
+    assert ctx.launch_count() - l0 == n_burst
+    assert ctx.class_launches(nat.KC_KMC_STEP) == n_burst and ctx.total_kernel_ms(nat.KC_KMC_STEP) > 0
+    in_flight = ens.read()
+    # batches A, B, A through the pipelined read-back: batch B starts from other sites
+    occ_b = K.philox_initial_occupancy(run.tables, n_traj, 64, seed=22)
+    bufs = [ens.pinned_buffers(), ens.pinned_buffers()]
+    outs = []
+    for i, o in enumerate((occ, occ_b, occ)):
+        ens.reset(o, 0)
+        for _ in range(n_burst):
+            ens.advance_async(burst)
+        if i > 0:
+            ens.read_end()
+            outs.append({k: (None if v is None else np.array(v)) for k, v in bufs[(i - 1) & 1].items()})
+        ens.read_begin(bufs[i & 1])
+    ens.read_end()
+    outs.append({k: (None if v is None else np.array(v)) for k, v in bufs[0].items()})
+    ens.close()
+    system.close()
+    ref = O.KmcOracle(run, dense, rng_mode=1, seed=21, **kw).ensemble(occ)
+    ref_b = O.KmcOracle(run, dense, rng_mode=1, seed=21, **kw).ensemble(occ_b)
+    for got, want in ((plain, ref), (in_flight, ref), (outs[0], ref), (outs[1], ref_b), (outs[2], ref)):
+        assert np.array_equal(got['n_steps'], want['n_steps'])
+        assert np.array_equal(got['occupancy'], want['occupancy'])
+        assert np.array_equal(got['unwrapped'], want['unwrapped'])
+    assert np.array_equal(plain['drift'], in_flight['drift']) and np.array_equal(plain['time'], outs[2]['time'])
+
+
 @pytest.mark.parametrize('carriers', [5, 33, 64, 100])
 def test_stencil_kernel_equals_gather_kernels(ctx, hematite_64e, carriers, monkeypatch):
     """The lattice-stencil kernel (one H[b_a][delta][b_y][slot] entry per carrier pair) against the
