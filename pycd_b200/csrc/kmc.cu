@@ -1240,7 +1240,7 @@ struct pycd_kmc_system {
     size_t st_smem = 0;
     DevBuf<double> st_H, st_cst;
     DevBuf<int> st_ctr_key, st_ctr_site, st_nbr_key, st_nbr_ctr, st_cb_all, st_nb_all, st_nb_cell;
-    DevBuf<unsigned long long> st_perm;
+    DevBuf<unsigned long long> st_perm, st_nbr_perm;
 };
 
 struct pycd_kmc_ensemble {
@@ -1404,6 +1404,12 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
     up_i(sys->st_nb_cell, nb_cell);
     sys->st_perm.alloc(perm.size());
     PYCD_CUDA(cudaMemcpyAsync(sys->st_perm.p, perm.data(), sizeof(unsigned long long) * perm.size(), cudaMemcpyHostToDevice, s));
+    // the permutation of every neighbour beside its key: a hop finds its new site's permutation in the shared
+    // tables instead of waiting for a global load on the owner's chain
+    std::vector<unsigned long long> nbr_perm((size_t)nc * nn);
+    for (size_t i = 0; i < nbr_perm.size(); ++i) nbr_perm[i] = perm[(size_t)(nbr_ctr[i] & 0xffffff)];
+    sys->st_nbr_perm.alloc(nbr_perm.size());
+    PYCD_CUDA(cudaMemcpyAsync(sys->st_nbr_perm.p, nbr_perm.data(), sizeof(unsigned long long) * nbr_perm.size(), cudaMemcpyHostToDevice, s));
     sys->st_H.alloc((size_t)entries * nnp);
     sys->st_cst.alloc((size_t)ncb * ST_ROWS * nn);
     stencil_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(
@@ -1417,7 +1423,7 @@ static void setup_stencil(pycd_kmc_system *sys, const pycd_kmc_system_desc *d, c
     PYCD_CUDA(cudaStreamSynchronize(s));   // the host vectors above are read by the async copies
     StencilDev &t = sys->st;
     t.H = sys->st_H.p; t.ctr_key = sys->st_ctr_key.p; t.ctr_site = sys->st_ctr_site.p;
-    t.nbr_key = sys->st_nbr_key.p; t.nbr_ctr = sys->st_nbr_ctr.p; t.perm = sys->st_perm.p; t.cst = sys->st_cst.p;
+    t.nbr_key = sys->st_nbr_key.p; t.nbr_ctr = sys->st_nbr_ctr.p; t.perm = sys->st_perm.p; t.nbr_perm = sys->st_nbr_perm.p; t.cst = sys->st_cst.p;
     t.ncb = ncb;
     t.rs_p1 = (int)(rs + 1);
     t.l0_ncb = (int)(((((long long)(sx - 1) * wy + (sy - 1)) * wz + (sz - 1))) * ncb);

@@ -107,6 +107,7 @@ struct StencilDev {
     const int *nbr_key;      // [n_centres][nn] K of the neighbour in REFERENCE slot s
     const int *nbr_ctr;      // [n_centres][nn] its centre index | basis << 24
     const unsigned long long *perm;   // [n_centres] 4 bits per canonical direction d: reference slot of d
+    const unsigned long long *nbr_perm;   // [n_centres][nn] perm of the neighbour in reference slot s (prefetched with the row)
     const double *cst;       // [ncb][ST_ROWS][nn]
     int ncb, rs_p1, l0_ncb;
 };
