@@ -18,15 +18,15 @@ OUT = ROOT / 'scratch' / 'ab'
 
 VARIANTS = {
     'default': [],
-    #'shuffle_scan_and_sums': ['-DPYCD_SCAN_DMMA=0', '-DPYCD_SUM_DMMA=0'],
-    #'helper_warp_off': ['-DPYCD_HELPER_WARP=0'],
-    #'flat_tail_off': ['-DPYCD_FLAT_TAIL=0'],
-    #'owner_late': ['-DPYCD_OWNER_EARLY=0'],
-    #'exp_table': ['-DPYCD_EXP_TABLE=1'],
+    'shuffle_scan_and_sums': ['-DPYCD_SCAN_DMMA=0', '-DPYCD_SUM_DMMA=0'],
+    'helper_warp_off': ['-DPYCD_HELPER_WARP=0'],
+    'flat_tail_off': ['-DPYCD_FLAT_TAIL=0'],
+    'owner_late': ['-DPYCD_OWNER_EARLY=0'],
+    'exp_table': ['-DPYCD_EXP_TABLE=1'],
     'perm_global_load': ['-DPYCD_PERM_PREFETCH=0'],
 }
 # a header from the history compiled against today's kmc_types.cuh: HEADER@<git rev>
-HISTORY = {'committed_e9c8ab9': 'e9c8ab9'}
+HISTORY = {}
 
 
 def build():
