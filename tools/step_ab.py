@@ -24,6 +24,8 @@ VARIANTS = {
     'owner_late': ['-DPYCD_OWNER_EARLY=0'],
     'exp_table': ['-DPYCD_EXP_TABLE=1'],
     'perm_global_load': ['-DPYCD_PERM_PREFETCH=0'],
+    'ld_l1_allocate': ['-DPYCD_LD_MODE=0'],
+    'ld_cg': ['-DPYCD_LD_MODE=5'],
 }
 # a header from the history compiled against today's kmc_types.cuh: HEADER@<git rev>
 HISTORY = {}
@@ -82,6 +84,7 @@ def run(trajs, repeats=3):
             d = json.loads(res.stdout.strip().splitlines()[-1])
             r = d['roofline']
             row = {'variant': name, 'rep': rep, 'traj': nt, 'kernel_ms': r['kernel_ms_per_launch'],
+                   'stateless_ms': (d.get('stateless') or {}).get('kernel_ms_per_launch'),
                    'cycles_per_step': r['latency']['cycles_per_kmc_step'], 'msteps_per_s': d['value'] / 1e6}
             rows.append(row)
             print(json.dumps(row), flush=True)
@@ -93,7 +96,9 @@ def run(trajs, repeats=3):
         for nt in trajs:
             v = [r['kernel_ms'] for r in rows if r['variant'] == name and r['traj'] == nt]
             if v:
-                print(f'{name:44s} traj {nt:4d}  median {statistics.median(v):.3f}  min {min(v):.3f}  ({len(v)} runs)')
+                sl = [r['stateless_ms'] for r in rows if r['variant'] == name and r['traj'] == nt and r['stateless_ms']]
+                print(f'{name:44s} traj {nt:4d}  median {statistics.median(v):.3f}  min {min(v):.3f}  ({len(v)} runs)'
+                      + (f'  stateless {statistics.median(sl):.2f}' if sl else ''))
 
 
 if __name__ == '__main__':

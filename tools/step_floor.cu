@@ -20,7 +20,11 @@
 
 __device__ __forceinline__ void ld256(const double *p, double (&v)[4])
 {
+#ifdef FLOOR_L1_ALLOCATE   // the step kernel's load before the no-allocate form (profiles/r02_step_floor_l1_allocate.json)
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#endif
 }
 
 __device__ __forceinline__ unsigned lcg(unsigned &s) { s = s * 1664525u + 1013904223u; return s; }
