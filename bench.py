@@ -114,10 +114,15 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
         except Exception:
             self.nv = None
+
+    def start(self):
+        """Begin sampling (the NVML set-up above takes milliseconds and stays outside the timed region)."""
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
 
     def _sample(self):
         nv = self.nv
@@ -432,6 +437,7 @@ def main():
             torch.cuda.synchronize()
 
     kernel_names = {}
+    region = {}     # per timed region: when this rank's launches were done, and what the closing barrier added
 
     def timed_run(refresh, steps, warmup):
         ens = K.KmcEnsemble(system, occ, dt_grid=dt_grid, n_path=args.n_path, step_limit=10 ** 12,
@@ -442,10 +448,14 @@ def main():
                 ctx.flush_l2()        # also allocates the 512 MB flush buffer outside the timed region
             ens.advance_async(S)
         ens.wait()
+        # NVML set-up before the opening barrier: done after it, it delayed rank 0's launches by ~5 ms and every
+        # other rank waited that long at the closing barrier
+        sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
         barrier()
         ctx.reset_timers()
         l0 = ctx.launch_count()
-        sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
+        if sampler:
+            sampler.start()
         t0 = time.perf_counter()
         # the launches are enqueued back to back (pycd_kmc_advance_async: no host round trip per launch, so
         # host jitter -- other ranks, the NVML sampler -- cannot open gaps between them); wait() + barrier
@@ -455,8 +465,10 @@ def main():
                 ctx.flush_l2()            # 512 MB memset between timed iterations (stream-ordered)
             ens.advance_async(S)
         ens.wait()
+        t_done = time.perf_counter() - t0
         barrier()
         wall = time.perf_counter() - t0
+        region[refresh] = {'own_launches_done_s': round(t_done, 5), 'closing_barrier_s': round(wall - t_done, 5)}
         clocks = sampler.stop() if sampler else None
         kern_ms = ctx.total_kernel_ms(nat.KC_KMC_STEP)
         launches = ctx.launch_count() - l0
@@ -650,7 +662,7 @@ def main():
                             '(double-buffered: the copy of batch k runs under batch k+1, pycd_kmc_read_begin/_end); '
                             'the Ewald table stays resident (uploaded once per material, like the reference '
                             'loads precomputed_array.npy once)'},
-            'gpu_launches': int(launches),
+            'gpu_launches': int(launches), 'timed_region_rank0': region.get(args.refresh),
             'clocks': clocks,
             'roofline': roofline,
             'cpu_baseline': cpu, 'parity_in_bench': parity_in_bench,
@@ -764,7 +776,7 @@ def single_config(args):
     if nat.needs_build():
         nat.build()
     ctx = nat.default_context(local_rank)
-    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
+    sampler = ClockSampler(local_rank).start() if (rank == 0 and not args.no_clocks) else None
     l0 = ctx.launch_count()
     if args.config == 2:
         res = BC.cfg2_bvo(ctx, dev, rank, world, dist, traj_per_gpu=args.traj_per_gpu, launches=max(args.steps, 1))

@@ -35,7 +35,7 @@ def main():
     with open(out, 'w') as f:
         f.write(f'# cuobjdump -sass -fun kmc_step_warp_kernel<2,1,4,INCR,PLAIN> {lib}\n')
         f.write(f'# burst loop: {len(body)} instructions, 0x{body[0][0]:04x} .. 0x{body[-1][0]:04x} (cold blocks included)\n')
-        for name, pat in (('DMMA.8x8x4 (warp scan: 4, direction sums: 5)', r'^DMMA'), ('LDG.E.ENL2.256.CONSTANT (table entries)', r'LDG\.E\.ENL2\.256'),
+        for name, pat in (('DMMA.8x8x4 (warp scan: 4, direction sums: 5)', r'^DMMA'), ('LDG.E.NA.ENL2.256.CONSTANT (table entries, no L1 allocation)', r'LDG\.E\.(NA\.)?ENL2\.256'),
                           ('REDUX.SUM (selection count)', r'^REDUX'), ('SHFL', r'SHFL'), ('BAR.SYNC', r'BAR\.SYNC'),
                           ('BSSY', r'^BSSY'), ('VOTE', r'^VOTE'), ('DFMA/DMUL/DADD', r'^D(FMA|MUL|ADD)'), ('MUFU.RCP64H (time advance division)', r'MUFU\.RCP64H'),
                           ('LDS', r'^(@!?U?P\d\s+)?LDS'), ('STS', r'^(@!?U?P\d\s+)?STS')):
