@@ -731,11 +731,12 @@ def reference_timed(args, run, P_host, N):
     wall = time.perf_counter() - t0
     value = tot / wall
     n_proc = C_ * run.tables.nn
+    sz = [int(v) for v in run.supercell.system_size]   # the build container (no GPU) times the shipped 2x2x1 cell
     line = {'impl': 'reference', 'metric': 'KMC steps/s (all trajectories, box-wide)', 'value': value,
             'unit': 'KMC steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': wall / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'Hematite {args.size[0]}x{args.size[1]}x{args.size[2]} supercell '
+            'config': {'workload': f'Hematite {sz[0]}x{sz[1]}x{sz[2]} supercell '
                                    f'(N={N}), {C_} electrons, Philox draws, fixed-step mode',
                        'n_proc': n_proc},
             'cpu_baseline': {'value': value, 'unit': 'KMC steps/s', 'cores': thr, 'kind': 'port',
