@@ -207,7 +207,10 @@ int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ensemble_desc 
                              pycd_kmc_ensemble **out);
 int pycd_kmc_ensemble_destroy(pycd_kmc_ensemble *ens);
 /* Re-arm an ensemble (same sizes and run parameters) with new initial sites: t = 0, empty
- * grid; avoids re-allocating the per-trajectory state between batches. */
+ * grid; avoids re-allocating the per-trajectory state between batches.  Stream-ordered: the sites are
+ * validated and staged before the call returns (the caller's buffer is free again), the copies and
+ * clears are enqueued behind the launches issued so far -- no host synchronisation, so the re-arm and
+ * the launches of the next batch can be issued while the current batch still runs. */
 int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *occupancy0, uint64_t traj_id0);
 
 /* Advance every unfinished trajectory by at most max_steps KMC steps: rate evaluation

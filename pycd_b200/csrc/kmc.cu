@@ -8,6 +8,7 @@
 // refresh_interval = 1 re-gathers every process every step (the stateless
 // formulation the roofline figure B_step counts); R > 1 patches the cached sums
 // after each hop (4 gathers per untouched process) and re-gathers every R steps.
+#include <cstring>
 #include "kmc_types.cuh"
 
 #include <algorithm>
@@ -1261,9 +1262,17 @@ struct pycd_kmc_ensemble {
     cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
     bool read_in_flight = false;
     bool needs_reset = false;   // the displacement grid was handed to a pipelined read: re-arm before advancing
+    // pycd_kmc_ensemble_reset without a host synchronisation: the new sites are staged in page-locked memory
+    // owned by the ensemble (the caller's buffer is free when the call returns), ev_stage guards its re-use
+    int *occ_stage = nullptr;
+    cudaEvent_t ev_stage = nullptr;
+    bool stage_in_flight = false;
+    DevBuf<long long> ones;     // start_path_index = 1 per trajectory (core.py:2781), source of the re-arm copy
     ~pycd_kmc_ensemble() {
         if (ev_snap) cudaEventDestroy(ev_snap);
         if (ev_copied) cudaEventDestroy(ev_copied);
+        if (ev_stage) cudaEventDestroy(ev_stage);
+        if (occ_stage) cudaFreeHost(occ_stage);
     }
 };
 
@@ -1614,6 +1623,8 @@ extern "C" int pycd_kmc_ensemble_create(pycd_kmc_system *sys, const pycd_kmc_ens
             ens->start_idx.alloc(nt);
             std::vector<long long> ones((size_t)nt, 1);  // start_path_index = 1, core.py:2781
             PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
+            ens->ones.alloc(nt);
+            PYCD_CUDA(cudaMemcpyAsync(ens->ones.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
             if (d->record_unwrapped) {
                 ens->unwrapped.alloc((size_t)nt * d->n_path * 3 * C);
                 ens->unwrapped.zero(s);
@@ -1723,19 +1734,26 @@ extern "C" int pycd_kmc_ensemble_reset(pycd_kmc_ensemble *ens, const int32_t *oc
         EnsDev &E = ens->dev;
         const size_t nt = (size_t)E.n_traj;
         cudaStream_t s = ctx->stream;
+        // stream-ordered, no host synchronisation: the re-arm of batch k+1 can be enqueued while batch k runs
+        if (!ens->occ_stage) {
+            PYCD_CUDA(cudaHostAlloc((void **)&ens->occ_stage, sizeof(int) * nt * E.C, cudaHostAllocDefault));
+            PYCD_CUDA(cudaEventCreateWithFlags(&ens->ev_stage, cudaEventDisableTiming));
+        }
+        if (ens->stage_in_flight) PYCD_CUDA(cudaEventSynchronize(ens->ev_stage));   // previous re-arm has left the stage
         std::vector<int> occ_h;
         validate_occupancy(ens->sys, occupancy0, nt * E.C, occ_h);
-        PYCD_CUDA(cudaMemcpyAsync(ens->occ.p, occupancy0, sizeof(int) * nt * E.C, cudaMemcpyDefault, s));
+        memcpy(ens->occ_stage, occ_h.data(), sizeof(int) * nt * E.C);
+        PYCD_CUDA(cudaMemcpyAsync(ens->occ.p, ens->occ_stage, sizeof(int) * nt * E.C, cudaMemcpyHostToDevice, s));
+        PYCD_CUDA(cudaEventRecord(ens->ev_stage, s));
+        ens->stage_in_flight = true;
         ens->done.zero(s); ens->t.zero(s); ens->disp.zero(s); ens->row.zero(s); ens->drift.zero(s);
         ens->rates.zero(s); ens->n_steps.zero(s); ens->near_tie.zero(s); ens->clamped.zero(s);
         ens->unwrapped.zero(s);
-        std::vector<long long> ones(nt, 1);
-        PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ones.data(), sizeof(long long) * nt, cudaMemcpyHostToDevice, s));
+        PYCD_CUDA(cudaMemcpyAsync(ens->start_idx.p, ens->ones.p, sizeof(long long) * nt, cudaMemcpyDeviceToDevice, s));
         E.traj_id0 = traj_id0;
         ens->n_active = -1;
         ens->needs_reset = false;
         arm_energy(ens, s);
-        PYCD_CUDA(cudaStreamSynchronize(s));
     });
 }
 

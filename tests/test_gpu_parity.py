@@ -418,16 +418,20 @@ def test_batch_production_api_equals_the_synchronous_calls(ctx, hematite_64e):
     occ_b = K.philox_initial_occupancy(run.tables, n_traj, 64, seed=22)
     bufs = [ens.pinned_buffers(), ens.pinned_buffers()]
     outs = []
-    for i, o in enumerate((occ, occ_b, occ)):
-        ens.reset(o, 0)
+    batches = (occ, occ_b, occ)
+
+    def launch(o):
+        ens.reset(o, 0)              # stream-ordered: enqueued behind whatever still runs
         for _ in range(n_burst):
             ens.advance_async(burst)
-        if i > 0:
-            ens.read_end()
-            outs.append({k: (None if v is None else np.array(v)) for k, v in bufs[(i - 1) & 1].items()})
+    launch(batches[0])
+    for i in range(3):
         ens.read_begin(bufs[i & 1])
-    ens.read_end()
-    outs.append({k: (None if v is None else np.array(v)) for k, v in bufs[0].items()})
+        if i + 1 < 3:
+            launch(batches[i + 1])   # the next batch is in the queue before the host waits for this one's copy
+        ens.read_end()
+        outs.append({k: (None if v is None else np.array(v)) for k, v in bufs[i & 1].items()})
+    assert ens.wait() == 0
     ens.close()
     system.close()
     ref = O.KmcOracle(run, dense, rng_mode=1, seed=21, **kw).ensemble(occ)
