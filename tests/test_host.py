@@ -356,3 +356,50 @@ def test_bench_cpu_legs_run_without_a_gpu():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+
+
+def test_sweep_host_logic():
+    """pycd_b200/sweep.py without a GPU: condition grid of BASELINE config 5, per-condition time grids that
+    equalise the step counts (Arrhenius ratio of k_total), and the per-condition reduction -- trajectory g
+    belongs to condition g % n_cond; diffusivity from the per-trajectory slopes (core.py:3052-3071), drift
+    mobility from the accumulated drift (core.py:2052-2082)."""
+    from pycd_b200 import sweep as SW
+    from pycd_b200 import kmc as K
+    conds = SW.hematite_conditions()
+    assert len(conds) == 8 and [c[0] for c in conds] == [250.0, 250.0, 300.0, 300.0, 350.0, 350.0, 400.0, 400.0]
+    assert not conds[0][1].any() and np.array_equal(conds[1][1], [1e-4, 0.0, 0.0])
+    n_path, steps, C_ = 1001, 20000, 64
+    iv = SW.balanced_intervals(conds, C_, steps, n_path)
+    assert np.array_equal(iv[0::2], iv[1::2])                       # the field does not change the grid
+    # at 300 K the grid spans steps / (C * 3.2e9 /s); the others follow the Arrhenius factor of the hop
+    t300 = steps / (C_ * 3.2e9) * constants.SEC2AUTIME / (n_path - 1)
+    assert np.isclose(iv[2], t300, rtol=1e-12)
+    ratio = np.exp(-0.252 / 8.617333262e-5 * (1 / 250.0 - 1 / 300.0))
+    assert np.isclose(iv[2] / iv[0], ratio, rtol=1e-12) and iv[0] > iv[2] > iv[4] > iv[6]
+    # synthetic per-trajectory arrays: condition c has slope (c + 1) A^2 per ns, replica r adds r percent
+    n_cond, reps, n_msd, trim = len(conds), 6, 41, 4
+    n_total = n_cond * reps
+    g = np.arange(n_total)
+    slope = (g % n_cond + 1.0) * (1.0 + 0.01 * (g // n_cond))
+    avg = np.empty((n_total, n_msd, 1))
+    for t in range(n_total):
+        dt_ns = iv[t % n_cond] * constants.AUTIME2NS
+        avg[t, :, 0] = slope[t] * np.arange(n_msd) * dt_ns
+    drift = np.zeros((n_total, C_, 3))
+    drift[:, :, 0] = (g % n_cond + 1.0)[:, None] * 1e-3
+    rows = SW.analyse_conditions(conds, iv, avg, drift, np.full(n_total, float(steps)), n_msd, trim)
+    assert [r['n_traj'] for r in rows] == [reps] * n_cond
+    for c, row in enumerate(rows):
+        T, f = conds[c]
+        kbt = constants.KB * T / constants.EV2J
+        sl = slope[g % n_cond == c]
+        want = sl.mean() * constants.ANG2CM ** 2 * constants.SEC2NS / 6 / kbt
+        assert np.isclose(row['D_cm2_per_Vs'], want, rtol=1e-9)
+        assert np.isclose(row['D_sem'], sl.std() / np.sqrt(reps) * constants.ANG2CM ** 2 * constants.SEC2NS / 6 / kbt, rtol=1e-7)
+        assert row['mean_steps'] == steps
+        if f.any():
+            mob = K.drift_mobility(drift[g % n_cond == c], f, float(np.linalg.norm(f))).mean(axis=1)
+            assert np.isclose(row['drift_mobility_cm2_per_Vs'], mob.mean(), rtol=1e-12)
+            assert row['drift_mobility_sem'] == 0.0 or row['drift_mobility_sem'] < 1e-12 * abs(mob.mean())
+        else:
+            assert 'drift_mobility_cm2_per_Vs' not in row
