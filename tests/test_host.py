@@ -247,6 +247,20 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert 'sm_100a' in sass
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/pycd_b200.h against the ctypes table of pycd_b200/_native.py: same number of
+    arguments (a mismatch would not fail at load time, it would corrupt a call)."""
+    header = (ROOT / 'include' / 'pycd_b200.h').read_text()
+    header = re.sub(r'/\*.*?\*/', ' ', header, flags=re.S)
+    protos = re.findall(r'\b(pycd_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', header, flags=re.S)
+    assert len(protos) == len(nat.EXPORTED_SYMBOLS)
+    for name, args in protos:
+        args = ' '.join(args.split())
+        n = 0 if args in ('', 'void') else args.count(',') + 1
+        assert name in nat._SIGNATURES, name
+        assert len(nat._SIGNATURES[name][1]) == n, (name, n, len(nat._SIGNATURES[name][1]))
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
