@@ -261,6 +261,29 @@ def test_ctypes_signatures_match_the_header():
         assert len(nat._SIGNATURES[name][1]) == n, (name, n, len(nat._SIGNATURES[name][1]))
 
 
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The four descriptor structs: size and the offset of every field as gcc lays them out from
+    include/pycd_b200.h against the ctypes mirrors (same field names, same order)."""
+    pairs = {'pycd_ewald_desc': nat.EwaldDesc, 'pycd_ewald_stats': nat.EwaldStats,
+             'pycd_kmc_system_desc': nat.KmcSystemDesc, 'pycd_kmc_ensemble_desc': nat.KmcEnsembleDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "pycd_b200.h"}"',
+             'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-o', str(exe), str(src)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
